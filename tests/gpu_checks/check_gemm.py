@@ -1,0 +1,145 @@
+"""Stand-alone GPU check of the tcgen05 GEMM / wgrad kernels against torch fp64 (run under gpurun).
+
+Not collected by pytest (no test_ prefix); tests/test_gemm_gpu.py holds the pytest version.
+"""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+lib = ctypes.CDLL(os.path.join(ROOT, "transformer-pointer-critic_b200", "libtpc.so"))
+P = ctypes.c_void_p
+I = ctypes.c_int
+lib.tpc_create.argtypes = [ctypes.POINTER(P)]
+lib.tpc_gemm.argtypes = [P, P, I, P, I, P, I, I, I, I, P, P, I, I, P, P, P, I, I, P]
+lib.tpc_wgrad.argtypes = [P, P, I, P, I, P, I, I, I, I, P]
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def tf32(x):
+    # round-to-nearest-even emulation is close enough to rna for a tolerance check
+    return (x.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32) if False else x
+
+
+def main():
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    h = P()
+    rc = lib.tpc_create(ctypes.byref(h))
+    assert rc == 0, rc
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    worst = 0.0
+    for (M, N, K) in [(128, 128, 128), (300, 128, 128), (1000, 384, 128), (4096, 128, 512), (777, 512, 128),
+                      (260, 128, 19328)]:
+        A = torch.randn(M, K, device=dev)
+        Bt = torch.randn(N, K, device=dev) / K ** 0.5
+        bias = torch.randn(N, device=dev)
+        D = torch.full((M, N), float("nan"), device=dev)
+        rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, ptr(bias), None, 0, 0, None, None, None, 0, 1,
+                          stream)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        ref = (A.double() @ Bt.double().T + bias.double())
+        err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"gemm  M={M} N={N} K={K}: rel-max err {err:.3e} finite={torch.isfinite(D).all().item()}")
+        worst = max(worst, err)
+
+    # relu + aux add + round
+    M, N, K = 555, 256, 128
+    A = torch.randn(M, K, device=dev)
+    Bt = torch.randn(N, K, device=dev) / K ** 0.5
+    aux = torch.randn(M, N, device=dev)
+    D = torch.empty(M, N, device=dev)
+    rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, ptr(aux), N, 1, None, None, None, 1, 1, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = torch.relu(A.double() @ Bt.double().T) + aux.double()
+    err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"gemm relu+add: {err:.3e}")
+    worst = max(worst, err)
+    # gate in place
+    Hm = torch.randn(M, N, device=dev)
+    D = Hm.clone()
+    rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, ptr(D), N, 2, None, None, None, 0, 1, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = (A.double() @ Bt.double().T) * (Hm.double() > 0)
+    err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"gemm gate in-place: {err:.3e}")
+    worst = max(worst, err)
+
+    # residual + layernorm
+    M, N, K = 1000, 128, 512
+    A = torch.randn(M, K, device=dev)
+    Bt = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    gamma = torch.rand(N, device=dev) + 0.5
+    beta = torch.randn(N, device=dev)
+    D = torch.empty(M, N, device=dev)
+    rstd = torch.empty(M, device=dev)
+    rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, ptr(bias), ptr(res), N, 1, ptr(gamma), ptr(beta),
+                      ptr(rstd), 2 | 4, 1, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    pre = A.double() @ Bt.double().T + bias.double() + res.double()
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma.double(), beta.double(), 1e-6)
+    err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+    rref = 1.0 / torch.sqrt(pre.var(dim=1, unbiased=False) + 1e-6)
+    rerr = ((rstd.double() - rref).abs() / rref).max().item()
+    print(f"gemm +res+LN: {err:.3e}  rstd {rerr:.3e}")
+    worst = max(worst, err)
+
+    # split-K atomic
+    M, N, K = 300, 128, 19328
+    A = torch.randn(M, K, device=dev)
+    Bt = torch.randn(N, K, device=dev) / K ** 0.5
+    D = torch.zeros(M, N, device=dev)
+    rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, None, 0, 0, None, None, None, 8, 40, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = A.double() @ Bt.double().T
+    err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"gemm split-K atomic: {err:.3e}")
+    worst = max(worst, err)
+
+    for (M, Kin, Nout) in [(256, 128, 128), (5000, 128, 384), (100000, 512, 128), (3000, 128, 512), (999, 1280, 128)]:
+        X = torch.randn(M, Kin, device=dev)
+        dY = torch.randn(M, Nout, device=dev)
+        dW = torch.zeros(Kin, Nout, device=dev)
+        rc = lib.tpc_wgrad(h, ptr(X), Kin, ptr(dY), Nout, ptr(dW), Nout, M, Kin, Nout, stream)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        ref = X.double().T @ dY.double()
+        err = (dW.double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"wgrad M={M} Kin={Kin} Nout={Nout}: rel-max err {err:.3e}")
+        worst = max(worst, err)
+
+    # timing of the common shape
+    M, N, K = 154624, 128, 128
+    A = torch.randn(M, K, device=dev)
+    Bt = torch.randn(N, K, device=dev)
+    D = torch.empty(M, N, device=dev)
+    for _ in range(3):
+        lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, None, 0, 0, None, None, None, 4, 1, stream)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(20):
+        lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, None, 0, 0, None, None, None, 4, 1, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"gemm {M}x{N}x{K}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s  {(M*K+M*N)*4/ms/1e6:.0f} GB/s")
+    print("WORST", worst)
+    assert worst < 2e-3, worst
+    print("OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,591 @@
+// tcgen05 (UMMA) TF32 GEMM kernels for sm_100a: TMA-fed, TMEM accumulators, warp-specialised, persistent.
+//
+//   gemm_tc_kernel  : D[M,N]  = epi(A[M,K] @ Bt[N,K]^T)       both operands K-major   (forward + dX)
+//   wgrad_tc_kernel : dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout]  both operands MN-major  (weight gradients)
+//
+// These carry every Dense layer of the reference model:
+//   agents/models/transformer/common/attention.py:33-35,50 (wq/wk/wv/dense),
+//   common/utils.py:8-11 (FFN), actor/decoder_layer.py:22-30, actor/pointer_attention.py:40-41 (W1/W2),
+//   critic/model.py:65-83 (final_layer0/1) and their backward passes (agents/trainer.py:115-141).
+//
+// Roles in a 256-thread CTA (one CTA per SM, persistent over work items):
+//   warp 0   : TMA producer (A/B k-blocks into a 4-stage smem ring, 128B-swizzled boxes of 32 fp32 columns)
+//   warp 1   : MMA issuer (one elected lane, tcgen05.mma kind::tf32, M=128 N=128 K=8 per instruction)
+//   warp 2   : TMEM allocator (2 x 128 columns: double-buffered accumulator)
+//   warps 4-7: epilogue (thread == accumulator row: tcgen05.ld, bias/ReLU/residual/LayerNorm in registers,
+//              swizzled smem staging tile, TMA store)
+#include "gemm_tc.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace tpc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 32;                        // fp32 columns per k-block == one 128-byte swizzle span
+constexpr int STAGES = 4;
+constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;   // A + B
+constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int TMEM_COLS = 256;
+
+constexpr int WG_TB = 32;                     // tokens per wgrad stage (4 MMAs of K=8)
+constexpr int WG_STAGES = 6;
+constexpr int WG_BOX_BYTES = WG_TB * BK * 4;  // 4 KB: 32 tokens x 32 features
+constexpr int WG_STAGE_BYTES = 8 * WG_BOX_BYTES;  // X: 4 boxes (128 features) + dY: 4 boxes
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+
+struct GemmArgs {
+  int M, N, K;
+  int n_tiles, k_splits, kb_per_split, num_items;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* rstd_out;
+  float* atomic_out;
+  int ld_out;
+  int aux_mode, relu, ln, round_out, atomic;
+  float ln_eps;
+};
+
+// byte offset of (row, col) inside the staging tile: 4 boxes [128 rows][32 cols], rows of 128 B, 16-byte chunks
+// XOR-swizzled with (row & 7) -- the layout TMA produces/consumes for CU_TENSOR_MAP_SWIZZLE_128B.
+__device__ __forceinline__ uint32_t epi_off(int row, int col4 /* col / 4 */) {
+  const int box = col4 >> 3;
+  const int chunk = (col4 & 7) ^ (row & 7);
+  return box * TILE_BYTES + row * 128 + chunk * 16;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmD,
+               const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* epi = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* auxfull = tempty + 2;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (g.aux_mode) tma_prefetch_desc(&tmAux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_init(auxfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int first = blockIdx.x;
+  const int step = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = first; item < g.num_items; item += step) {
+        const int n_t = item % g.n_tiles;
+        const int rest = item / g.n_tiles;
+        const int ks = rest % g.k_splits;
+        const int m_t = rest / g.k_splits;
+        const int kb0 = ks * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = ring + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
+          tma_load_2d(sa + TILE_BYTES, &tmB, &full[stage], kb * BK, n_t * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = first; item < g.num_items; item += step, ++it) {
+        const int rest = item / g.n_tiles;
+        const int ks = rest % g.k_splits;
+        const int kb0 = ks * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sa + TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // advance 8 fp32 (32 B) along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+            umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem stage when these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);      // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int et = threadIdx.x - 128;          // 0..127 == accumulator row inside the tile == TMEM lane
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const bool leader = (et == 0);
+    uint32_t aux_phase = 0;
+    if (g.aux_mode && leader && first < g.num_items) {
+      const int n_t = first % g.n_tiles;
+      const int m_t = (first / g.n_tiles) / g.k_splits;
+      mbar_expect_tx(auxfull, EPI_BYTES);
+      for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, m_t * BM);
+    }
+    int it = 0;
+    for (int item = first; item < g.num_items; item += step, ++it) {
+      const int n_t = item % g.n_tiles;
+      const int m_t = (item / g.n_tiles) / g.k_splits;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m_t * BM + et;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (g.aux_mode) {
+        mbar_wait(auxfull, aux_phase);
+        aux_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+
+      if (g.atomic) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          if (row < g.M) {
+            float* dst = g.atomic_out + (size_t)row * g.ld_out + n_t * BN + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+      }
+
+      if (g.ln) {
+        // whole row (N == 128) in registers: bias + residual, two-pass mean / variance, scale + shift
+        float v[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + c * 32, v + c * 32);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator drained: MMA may start the next-but-one tile
+        float sum = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 32; ++c4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.aux_mode == 1) a = *reinterpret_cast<const float4*>(epi + epi_off(et, c4));
+          const float4 b = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[c4 * 4 + 0] += a.x + b.x;
+          v[c4 * 4 + 1] += a.y + b.y;
+          v[c4 * 4 + 2] += a.z + b.z;
+          v[c4 * 4 + 3] += a.w + b.w;
+          sum += (v[c4 * 4 + 0] + v[c4 * 4 + 1]) + (v[c4 * 4 + 2] + v[c4 * 4 + 3]);
+        }
+        const float mean = sum * (1.0f / 128.0f);
+        float ssq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const float d = v[j] - mean;
+          ssq = fmaf(d, d, ssq);
+        }
+        const float rstd = 1.0f / sqrtf(ssq * (1.0f / 128.0f) + g.ln_eps);
+        if (g.rstd_out && row < g.M) g.rstd_out[row] = rstd;
+#pragma unroll
+        for (int c4 = 0; c4 < 32; ++c4) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(g.gamma) + c4);
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(g.beta) + c4);
+          float4 o;
+          o.x = (v[c4 * 4 + 0] - mean) * rstd * gm.x + bt.x;
+          o.y = (v[c4 * 4 + 1] - mean) * rstd * gm.y + bt.y;
+          o.z = (v[c4 * 4 + 2] - mean) * rstd * gm.z + bt.z;
+          o.w = (v[c4 * 4 + 3] - mean) * rstd * gm.w + bt.w;
+          if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+          *reinterpret_cast<float4*>(epi + epi_off(et, c4)) = o;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int c4 = c * 8 + j4;
+            float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            if (g.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c4);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (g.aux_mode) {
+              const float4 a = *reinterpret_cast<const float4*>(epi + epi_off(et, c4));
+              if (g.aux_mode == 1) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+              else { o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f; }
+            }
+            if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+            *reinterpret_cast<float4*>(epi + epi_off(et, c4)) = o;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+
+      // staging tile complete -> TMA store (rows beyond M are clipped by the tensor map)
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+        for (int j = 0; j < 4; ++j) tma_store_2d(&tmD, epi + j * TILE_BYTES, n_t * BN + j * BK, m_t * BM);
+        tma_store_commit();
+        tma_store_wait_read0();  // staging tile may be overwritten
+        const int next = item + step;
+        if (g.aux_mode && next < g.num_items) {
+          const int nn = next % g.n_tiles;
+          const int nm = (next / g.n_tiles) / g.k_splits;
+          mbar_expect_tx(auxfull, EPI_BYTES);
+          for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, nn * BN + j * BK, nm * BM);
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+    if (leader) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient: D[Kin-tile 128][Nout-tile 128] += sum over tokens of X[t][ki*128+i] * dY[t][nj*128+j]
+// Operands are the raw row-major activation tiles (token rows of 128 B per 32-feature box) consumed as
+// MN-major UMMA operands: LBO = distance between 32-feature boxes, 8 tokens (two 4-token swizzle atoms) per MMA.
+// ---------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  int M, Kin, Nout;
+  int ki_tiles, nj_tiles, splits, tok_per_split, num_items;
+  float* dst[4];
+  int ld[4];
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const WgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WG_STAGES;
+  uint64_t* tfull = bars + 2 * WG_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int first = blockIdx.x;
+  const int step = gridDim.x;
+
+  // item -> (ki, nj, split); nj fastest so CTAs running side by side share the X token block in L2
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = first; item < g.num_items; item += step) {
+        const int nj = item % g.nj_tiles;
+        const int rest = item / g.nj_tiles;
+        const int ki = rest % g.ki_tiles;
+        const int sp = rest / g.ki_tiles;
+        const int t0 = sp * g.tok_per_split;
+        const int t1 = min(t0 + g.tok_per_split, g.M);
+        for (int t = t0; t < t1; t += WG_TB) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], WG_STAGE_BYTES);
+          uint8_t* sx = ring + stage * WG_STAGE_BYTES;
+          for (int j = 0; j < 4; ++j) tma_load_2d(sx + j * WG_BOX_BYTES, &tmX, &full[stage], ki * 128 + j * BK, t);
+          for (int j = 0; j < 4; ++j)
+            tma_load_2d(sx + (4 + j) * WG_BOX_BYTES, &tmY, &full[stage], nj * 128 + j * BK, t);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = first; item < g.num_items; item += step, ++it) {
+        const int sp = (item / g.nj_tiles) / g.ki_tiles;
+        const int t0 = sp * g.tok_per_split;
+        const int t1 = min(t0 + g.tok_per_split, g.M);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 128;
+        for (int t = t0; t < t1; t += WG_TB) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sx = smem_u32(ring + stage * WG_STAGE_BYTES);
+          // MN-major TF32 must use the 128B swizzle with 32-byte atoms (4-token K atom):
+          // LBO = next 32-feature box (4 KB), SBO = next 4-token group (512 B)
+          const uint64_t da = umma_smem_desc(sx, WG_BOX_BYTES, 512, 1);
+          const uint64_t db = umma_smem_desc(sx + 4 * WG_BOX_BYTES, WG_BOX_BYTES, 512, 1);
+#pragma unroll
+          for (int k = 0; k < WG_TB / 8; ++k) {
+            // next 8 tokens: +1024 B -> +64 in the (addr >> 4) field
+            umma_tf32_ss(tmem_d, da + 64 * k, db + 64 * k, idesc, (t > t0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    int it = 0;
+    for (int item = first; item < g.num_items; item += step, ++it) {
+      const int nj = item % g.nj_tiles;
+      const int ki = (item / g.nj_tiles) % g.ki_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * 128;
+      const int row = ki * 128 + et;
+      float* dst = g.dst[nj] + (size_t)row * g.ld[nj];
+      const int ncols = min(128, g.Nout - nj * 128);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (row < g.Kin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < ncols) atomicAdd(dst + c * 32 + j, v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launchers
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_init_once;
+int g_init_rc = TPC_OK;
+
+}  // namespace
+
+struct TmapCache {
+  std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> maps;
+  std::mutex mu;
+};
+TmapCache* tmap_cache_create() { return new TmapCache(); }
+void tmap_cache_destroy(TmapCache* c) { delete c; }
+
+int gemm_tc_init() {
+  std::call_once(g_init_once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "[tpc] cuTensorMapEncodeTiled not available (%s)\n", cudaGetErrorString(e));
+      g_init_rc = TPC_ERR_DRIVER;
+      return;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "[tpc] cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e));
+      g_init_rc = TPC_ERR_CUDA;
+    }
+  });
+  return g_init_rc;
+}
+
+// 2-D fp32 row-major [rows][cols] (leading dimension ld floats), box = [box_rows][32 cols], 128B swizzle.
+// atom32 selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major TF32 operands of the wgrad kernel).
+static int get_tmap(TmapCache* tc, const float* ptr, int rows, int cols, int ld, int box_rows, int atom32,
+                    CUtensorMap* out) {
+  auto key = std::make_tuple((const void*)ptr, rows, cols, ld, box_rows, atom32);
+  std::lock_guard<std::mutex> lk(tc->mu);
+  auto it = tc->maps.find(key);
+  if (it != tc->maps.end()) {
+    *out = it->second;
+    return TPC_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 4) != 0) {
+    fprintf(stderr, "[tpc] tensor map: pointer/ld not 16-byte aligned (ptr=%p ld=%d)\n", (const void*)ptr, ld);
+    return TPC_ERR_ARG;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[tpc] cuTensorMapEncodeTiled failed: %d (rows=%d cols=%d ld=%d box_rows=%d)\n", (int)r, rows,
+            cols, ld, box_rows);
+    return TPC_ERR_DRIVER;
+  }
+  if (tc->maps.size() > 4096) tc->maps.clear();
+  tc->maps[key] = m;
+  *out = m;
+  return TPC_OK;
+}
+
+int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream) {
+  TPC_TRY(gemm_tc_init());
+  if (M <= 0) return TPC_OK;
+  if (N % BN != 0 || K % BK != 0 || K <= 0) return TPC_ERR_SHAPE;
+  if (epi.ln && (N != BN || !epi.gamma || !epi.beta)) return TPC_ERR_SHAPE;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > 1 && !epi.atomic) return TPC_ERR_ARG;
+  if (epi.atomic && (epi.aux_mode || epi.ln || epi.relu || epi.bias)) return TPC_ERR_ARG;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.n_tiles = N / BN;
+  const int kblocks = K / BK;
+  g.kb_per_split = ceil_div(kblocks, k_splits);
+  g.k_splits = ceil_div(kblocks, g.kb_per_split);
+  g.num_items = ceil_div(M, BM) * g.n_tiles * g.k_splits;
+  g.bias = epi.bias; g.gamma = epi.gamma; g.beta = epi.beta; g.rstd_out = epi.rstd_out;
+  g.atomic_out = D; g.ld_out = ldd;
+  g.aux_mode = epi.aux_mode; g.relu = epi.relu; g.ln = epi.ln; g.round_out = epi.round_out; g.atomic = epi.atomic;
+  g.ln_eps = epi.ln_eps;
+  CUtensorMap tA, tB, tAux, tD;
+  TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
+  TPC_TRY(get_tmap(tc, Bt, N, K, ldb, BN, 0, &tB));
+  TPC_TRY(get_tmap(tc, D, M, N, ldd, BM, 0, &tD));
+  if (epi.aux_mode) {
+    if (!epi.aux) return TPC_ERR_ARG;
+    TPC_TRY(get_tmap(tc, epi.aux, M, N, epi.ldaux, BM, 0, &tAux));
+  } else {
+    tAux = tD;
+  }
+  const int grid = g.num_items < num_sms ? g.num_items : num_sms;
+  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA, tB, tAux, tD, g);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int launch_wgrad(TmapCache* tc, const float* X, int ldx, const float* dY, int ldy, int M, int Kin, int Nout,
+                 const WgradDst& dst, int num_sms, cudaStream_t stream) {
+  TPC_TRY(gemm_tc_init());
+  if (M <= 0) return TPC_OK;
+  if (Kin % BK != 0 || Nout % BK != 0) return TPC_ERR_SHAPE;
+  WgradArgs g;
+  g.M = M; g.Kin = Kin; g.Nout = Nout;
+  g.ki_tiles = ceil_div(Kin, 128);
+  g.nj_tiles = ceil_div(Nout, 128);
+  if (g.nj_tiles > 4) return TPC_ERR_SHAPE;
+  const int out_tiles = g.ki_tiles * g.nj_tiles;
+  // enough token splits to fill the machine, at least 256 tokens (8 stages) per split
+  int splits = ceil_div(2 * num_sms, out_tiles);
+  const int max_splits = ceil_div(M, 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  g.tok_per_split = ceil_div(ceil_div(M, splits), WG_TB) * WG_TB;
+  g.splits = ceil_div(M, g.tok_per_split);
+  g.num_items = out_tiles * g.splits;
+  for (int j = 0; j < 4; ++j) { g.dst[j] = dst.ptr[j]; g.ld[j] = dst.ld[j]; }
+  CUtensorMap tX, tY;
+  TPC_TRY(get_tmap(tc, X, M, Kin, ldx, WG_TB, 1, &tX));
+  TPC_TRY(get_tmap(tc, dY, M, Nout, ldy, WG_TB, 1, &tY));
+  const int grid = g.num_items < num_sms ? g.num_items : num_sms;
+  wgrad_tc_kernel<<<grid, GEMM_THREADS, WG_SMEM, stream>>>(tX, tY, g);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+}  // namespace tpc

@@ -1,0 +1,43 @@
+// Host-side interface of the tcgen05 GEMM kernels (implemented in gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tpc {
+
+// Epilogue of   D[M,N] = epi( A[M,K] @ Bt[N,K]^T )   (both operands K-major, fp32 storage, TF32 MMA)
+struct GemmEpi {
+  const float* bias = nullptr;    // [N]
+  const float* gamma = nullptr;   // LayerNorm scale [N]   (ln != 0, requires N == 128)
+  const float* beta = nullptr;    // LayerNorm shift [N]
+  float* rstd_out = nullptr;      // [M] 1/sqrt(var+eps) per row (saved for backward), optional
+  const float* aux = nullptr;     // [M,N] (ld = ldaux) second input of the epilogue
+  int ldaux = 0;
+  int aux_mode = 0;               // 0 none | 1 v += aux (residual / grad accumulation) | 2 v = aux > 0 ? v : 0 (ReLU bwd)
+  int relu = 0;                   // v = max(v, 0) after bias
+  int ln = 0;                     // LayerNorm over the row after bias + aux
+  int round_out = 1;              // store RN-rounded TF32 values (the output feeds a tensor-core operand)
+  int atomic = 0;                 // split-K: atomically accumulate into D (D pre-initialised), no other epilogue op
+  float ln_eps = 1e-6f;
+};
+
+// Caches CUtensorMap objects per (pointer, shape, box); owned by the library handle.
+struct TmapCache;
+TmapCache* tmap_cache_create();
+void tmap_cache_destroy(TmapCache*);
+
+int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes. idempotent.
+
+// D[M,N] = epi(A[M,K] @ Bt[N,K]^T). K % 32 == 0, N % 128 == 0. k_splits > 1 requires epi.atomic.
+int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream);
+
+// dW[nj][Kin, 128] += X[M,Kin]^T @ dY[M, nj*128 .. nj*128+127]  for every 128-wide column tile nj of dY.
+// dptr[nj] is the destination of tile nj with leading dimension ldd[nj]; accumulation is atomic.
+struct WgradDst {
+  float* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ld[4] = {0, 0, 0, 0};
+};
+int launch_wgrad(TmapCache* tc, const float* X, int ldx, const float* dY, int ldy, int M, int Kin, int Nout,
+                 const WgradDst& dst, int num_sms, cudaStream_t stream);
+
+}  // namespace tpc

@@ -1,0 +1,72 @@
+// C-ABI entry points for the stand-alone operators (unit-test granularity): tensor-core GEMMs.
+// Declared in include/tpc.h.
+#include "handle.cuh"
+
+using namespace tpc;
+
+extern "C" {
+
+int tpc_create(tpc_handle** out) {
+  if (!out) return TPC_ERR_ARG;
+  int dev = 0;
+  TPC_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TPC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    fprintf(stderr, "[tpc] this library is built for sm_100a only (device is sm_%d%d)\n", prop.major, prop.minor);
+    return TPC_ERR_DRIVER;
+  }
+  TPC_TRY(gemm_tc_init());
+  tpc_handle* h = new tpc_handle();
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  h->tmaps = tmap_cache_create();
+  *out = h;
+  return TPC_OK;
+}
+
+int tpc_destroy(tpc_handle* h) {
+  if (!h) return TPC_OK;
+  tmap_cache_destroy(h->tmaps);
+  delete h;
+  return TPC_OK;
+}
+
+int tpc_num_sms(const tpc_handle* h) { return h ? h->num_sms : 0; }
+
+// D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags: bit0 relu, bit1 layernorm(+rstd), bit2 round_out,
+// bit3 atomic split-K; aux_mode 0/1/2 (none / add / relu-gate).
+int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+             const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
+             float* rstd_out, int flags, int k_splits, void* stream) {
+  if (!h) return TPC_ERR_ARG;
+  GemmEpi e;
+  e.bias = bias;
+  e.aux = aux;
+  e.ldaux = ldaux;
+  e.aux_mode = aux_mode;
+  e.gamma = gamma;
+  e.beta = beta;
+  e.rstd_out = rstd_out;
+  e.relu = (flags & 1) ? 1 : 0;
+  e.ln = (flags & 2) ? 1 : 0;
+  e.round_out = (flags & 4) ? 1 : 0;
+  e.atomic = (flags & 8) ? 1 : 0;
+  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream);
+}
+
+// dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout]   (dW row-major with leading dimension ldw, atomically accumulated)
+int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int M, int Kin,
+              int Nout, void* stream) {
+  if (!h) return TPC_ERR_ARG;
+  WgradDst d;
+  const int nj = ceil_div(Nout, 128);
+  if (nj > 4) return TPC_ERR_SHAPE;
+  for (int j = 0; j < nj; ++j) {
+    d.ptr[j] = dW + j * 128;
+    d.ld[j] = ldw;
+  }
+  return launch_wgrad(h->tmaps, X, ldx, dY, ldy, M, Kin, Nout, d, h->num_sms, (cudaStream_t)stream);
+}
+
+}  // extern "C"
