@@ -1,0 +1,197 @@
+/* libtpc.so -- C-ABI of the B200-native rollout + A2C-update hot path of transformer-pointer-critic.
+ *
+ * The reference (AndreMaz/transformer-pointer-critic) is a pure-Python/TensorFlow program with no FFI; its
+ * seam is the Python object protocol between agents/trainer.py, environment/custom/resource_v3/tester.py and
+ * the Agent / env objects. Each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository). INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (torch-allocated) unless marked HOST;
+ * every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 or a negative TPC_ERR_*
+ * code, never throws; no global mutable state; a handle / model is not thread-safe, different ones are.
+ * All floating-point tensors are fp32, row-major; masks are fp32 with 1 = masked (as in the reference).
+ */
+#ifndef TPC_H_
+#define TPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPC_OK 0
+#define TPC_ERR_CUDA -1
+#define TPC_ERR_ARG -2
+#define TPC_ERR_SHAPE -3
+#define TPC_ERR_WORKSPACE -4
+#define TPC_ERR_DRIVER -5
+
+typedef struct tpc_handle tpc_handle;
+typedef struct tpc_model tpc_model;
+
+/* ------------------------------------------------------------------------------------------------------
+ * configuration (configs/ResourceV3.json:90-164, configs/KnapsackV2.json; agents/models/model_factory.py:4-36;
+ * environment/custom/resource_v3/env.py:21-81,314-334)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct tpc_model_config {
+  int actor_num_layers, actor_inner_layer_dim;     /* actor.num_layers, actor.inner_layer_dim */
+  int critic_num_layers, critic_inner_layer_dim;   /* critic.num_layers, critic.inner_layer_dim */
+  int dim_model, num_heads;                        /* must be 128 / 8 (all shipped configs) */
+  int attention_dense_units, last_layer_units;     /* must be 128 */
+  float logit_clipping_C;                          /* actor.logit_clipping_C */
+  int has_logit_clipping;                          /* 0 when logit_clipping_C is null */
+  int common_embedding;                            /* encoder_embedding.common (env.py:323-332) */
+  int num_bin_features, num_resource_features;     /* 3/3 ResourceV3, 4/3 "cost" reward, 2/2 KnapsackV2 */
+  int dec_features;                                /* decoder-input width = env num_features */
+  int num_bins, num_resources;                     /* TRAINING shape: critic Flatten width (critic/model.py:65) */
+} tpc_model_config;
+
+enum { TPC_ENV_RESOURCE_V3 = 0, TPC_ENV_KNAPSACK_V2 = 1 };
+enum { TPC_REWARD_GREEDY = 0, TPC_REWARD_SINGLE_NODE_DOMINANT = 1, TPC_REWARD_GLOBAL_DOMINANT = 2,
+       TPC_REWARD_REDUCED_NODE_USAGE = 3 };
+
+typedef struct tpc_env_config {
+  int kind;                    /* TPC_ENV_* */
+  int reward_type;             /* TPC_REWARD_* (environment/custom/resource_v3/reward.py:6-21) */
+  float rejection_penalty;     /* reward.<type>.rejection_penalty */
+  float use_new_node_penalty;  /* reward.reduced_node_usage.use_new_node_penalty */
+  int mask_nodes_in_mha;       /* env_config.mask_nodes_in_mha (env.py:153-156) */
+  int num_features;            /* 3 (ResourceV3) or 2 (KnapsackV2) */
+  float eos_code;              /* EOS_CODE (-2) */
+  /* instance generation (env.py:205-263): integers / normalization_factor */
+  int normalization_factor;
+  int node_min_val, node_max_val;  /* nodes: U{min..max-1} ; KnapsackV2: bin capacity */
+  int req_min_val, req_max_val;    /* rules: U{min..max-1} ; KnapsackV2: item weight */
+  int val_min_val, val_max_val;    /* KnapsackV2 only: item value */
+  int num_profiles;                /* profile table rows (0 => generate_request_on_the_fly) */
+} tpc_env_config;
+
+/* ------------------------------------------------------------------------------------------------------
+ * library + model objects
+ * ---------------------------------------------------------------------------------------------------- */
+int tpc_create(tpc_handle** out);
+int tpc_destroy(tpc_handle* h);
+int tpc_num_sms(const tpc_handle* h);
+
+/* replaces model_factory('transformer', opts) (agents/models/model_factory.py:4-36) */
+int tpc_model_create(tpc_handle* h, const tpc_model_config* cfg, tpc_model** out);
+int tpc_model_destroy(tpc_model* m);
+/* which: 0 actor, 1 critic. Canonical flat parameter vector (Keras trainable_weights order). */
+size_t tpc_param_count(const tpc_model* m, int which);
+int tpc_num_tensors(const tpc_model* m, int which);
+/* HOST out arrays of length tpc_num_tensors: offset and size of each canonical tensor */
+int tpc_param_layout(const tpc_model* m, int which, int64_t* offsets, int64_t* sizes);
+/* floats in the kernel-side weight image (transposed / fused / TF32-rounded copies) */
+size_t tpc_shadow_count(const tpc_model* m, int which);
+/* rebuild the weight image after params changed (after load_weights / every optimizer step) */
+int tpc_prepare_weights(tpc_model* m, int which, const float* params, float* shadow, void* stream);
+
+/* bytes of scratch a call needs for `nstates` states of shape (num_bins + num_resources) tokens.
+ * mode 0: actor forward (rollout step)   1: critic forward   2: actor forward+backward   3: critic fwd+bwd
+ *      4: tpc_rollout of nstates episodes */
+size_t tpc_workspace_bytes(const tpc_model* m, int mode, int nstates, int num_bins, int num_resources);
+
+/* workspace of tpc_rollout = tpc_workspace_bytes(m, 4, B, ...); of tpc_a2c_grads: */
+size_t tpc_a2c_workspace_bytes(const tpc_model* m, int B, int num_bins, int num_resources, int chunk_states);
+
+/* ------------------------------------------------------------------------------------------------------
+ * stand-alone operators (unit-test granularity)
+ * ---------------------------------------------------------------------------------------------------- */
+/* D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags bit0 relu, bit1 layernorm(gamma,beta -> rstd_out),
+ * bit2 round outputs to TF32, bit3 atomic split-K accumulate; aux_mode 0 none / 1 add / 2 relu-gate */
+int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+             const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
+             float* rstd_out, int flags, int k_splits, void* stream);
+/* dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout] */
+int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int M, int Kin,
+              int Nout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * model forward passes (step-wise, API-exact mode used by Agent.act / tests)
+ * ---------------------------------------------------------------------------------------------------- */
+/* replaces ActorTransformer.call (agents/models/transformer/actor/model.py:41-72) as used by Agent.act
+ * (agents/agent.py:265-273): state (B,S,Fstate) with Fstate = num_bin_features when not common_embedding
+ * (4th column = is_empty) else dec_features; dec_input (B,dec_features); ptr_mask (B,S) = feasible mask;
+ * mha_mask (B,S). Outputs: logits (B,S), probs (B,S), argmax (B) int32 (argmax over probs, lowest index wins). */
+int tpc_actor_forward(tpc_model* m, const float* shadow, const float* params, const float* state,
+                      const float* dec_input, const float* ptr_mask, const float* mha_mask, int B, int num_bins,
+                      int num_resources, float* logits, float* probs, int32_t* argmax, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* replaces CriticTransformer.call (agents/models/transformer/critic/model.py:55-85): values (nstates) */
+int tpc_critic_forward(tpc_model* m, const float* shadow, const float* params, const float* state,
+                       const float* mha_mask, int nstates, int num_bins, int num_resources, float* values,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * environment (environment/custom/resource_v3/env.py, reward.py, misc/utils.py; knapsack_v2/env.py)
+ * ---------------------------------------------------------------------------------------------------- */
+/* replaces generate_dataset (env.py:205-215): profiles (num_profiles, F) = U{req_min..req_max-1}/norm.
+ * Philox4x32-10, key = seed. */
+int tpc_env_generate_profiles(tpc_handle* h, const tpc_env_config* e, uint64_t seed, float* profiles, void* stream);
+/* replaces reset()/generate_batch()/generate_masks() (env.py:83-99,217-288): batch (B,S,F) with row 0 = EOS,
+ * bin_net_mask (B,S), mha_mask (B,S), is_empty (B,S) (reduced_node_usage only, may be NULL otherwise).
+ * Episode b uses the Philox stream (seed, episode_id0 + b, epoch) => independent of the GPU count. */
+int tpc_env_reset(tpc_handle* h, const tpc_env_config* e, uint64_t seed, int64_t episode_id0, int64_t epoch,
+                  const float* profiles, int B, int num_bins, int num_resources, float* batch, float* bin_net_mask,
+                  float* mha_mask, float* is_empty, void* stream);
+/* replaces build_feasible_mask (env.py:387-422): state (B,S,ld_state>=F), dec_input (B,F) */
+int tpc_env_feasible_mask(tpc_handle* h, const tpc_env_config* e, const float* state, int ld_state,
+                          const float* dec_input, const float* bin_net_mask, int B, int S, float* out_mask,
+                          void* stream);
+/* replaces step (env.py:115-203): in-place on batch / bin_net_mask / resource_net_mask (may be NULL) / mha_mask /
+ * is_empty; decoding_step = index of the rule being placed; reward (B). */
+int tpc_env_step(tpc_handle* h, const tpc_env_config* e, float* batch, float* bin_net_mask, float* resource_net_mask,
+                 float* mha_mask, float* is_empty, const int32_t* bin_ids, int decoding_step, int B, int num_bins,
+                 int num_resources, float* reward, void* stream);
+/* replaces tfp.distributions.Categorical(probs).sample() (agents/agent.py:275-280): inverse-CDF draw with the
+ * Philox uniform (seed, episode_id0 + b, draw_index). */
+int tpc_sample_categorical(tpc_handle* h, const float* probs, int B, int S, uint64_t seed, int64_t episode_id0,
+                           int64_t draw_index, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * fused fast path: rollout + A2C update (agents/trainer.py:37-175 behind one call each)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct tpc_rollout_buffers {
+  /* live environment state (in/out): as produced by tpc_env_reset */
+  float* batch; float* bin_net_mask; float* mha_mask; float* is_empty;
+  /* trajectory memory = Agent.store (agents/agent.py:75-95), step-major: */
+  float* states;       /* (T,B,S,F)      may be NULL in testing mode */
+  float* is_empties;   /* (T,B,S)        reduced_node_usage only, else NULL */
+  float* dec_inputs;   /* (T,B,F) */
+  float* ptr_masks;    /* (T,B,S) feasible masks returned by act */
+  float* mha_masks;    /* (T,B,S) */
+  int32_t* actions;    /* (T,B) */
+  float* rewards;      /* (B,T) */
+  float* logits;       /* (T,B,S) optional, may be NULL */
+} tpc_rollout_buffers;
+
+/* T = num_resources steps of {feasible mask -> actor forward -> greedy / sampled pick -> env step}. */
+int tpc_rollout(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
+                const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources, int greedy, uint64_t seed,
+                int64_t episode_id0, int64_t epoch, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct tpc_a2c_hyper {
+  float gamma, values_loss_coefficient, entropy_coefficient;  /* agents/agent.py:31-33 */
+  int chunk_states;       /* states per forward/backward chunk (0 = default) */
+  int total_states;       /* T*B of the WHOLE job (all ranks): denominator of both mean losses */
+} tpc_a2c_hyper;
+
+/* compute_discounted_rewards + compute_value_loss + compute_actor_loss + both GradientTapes
+ * (agents/agent.py:110-242, agents/trainer.py:103-141). Gradients are ACCUMULATED into actor_grads /
+ * critic_grads (canonical order; caller zeroes them, all-reduces them across ranks, then calls tpc_adam_apply).
+ * losses[4] (device): sum over local states of {(R-V)^2 * c_v, policy_loss, total actor loss, entropy}. */
+int tpc_a2c_grads(tpc_model* m, const float* actor_shadow, const float* actor_params, const float* critic_shadow,
+                  const float* critic_params, const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources,
+                  const tpc_a2c_hyper* hp, float* actor_grads, float* critic_grads, float* values, float* advantages,
+                  float* losses, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Keras Adam with per-variable clipnorm (agents/agent.py:39-49): clipnorm <= 0 disables it.
+ * step is 1-based. grad_scale multiplies the gradients first (1/world_size after a sum all-reduce). */
+int tpc_adam_apply(tpc_model* m, int which, float* params, const float* grads, float* adam_m, float* adam_v, int step,
+                   float lr, float clipnorm, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPC_H_ */

@@ -1,0 +1,311 @@
+// Multi-head self-attention of one encoder stack for sequences of at most 208 tokens (the reference tops out at
+// 151 = 51 nodes + 100 rules): K/V (or Q/dO) of one state staged in shared memory, one warp per head,
+// QK^T / PV on the legacy warp-level tensor path (mma.sync m16n8k8 TF32, fp32 accumulate), softmax with
+// warp shuffles in registers.  Restates common/attention.py:37-48 + common/utils.py:31-45 (forward) and the
+// autodiff of the same ops (agents/trainer.py:115-141).
+//
+// head_dim = 16 makes each head a K=16 contraction: far too thin for a 128-row tcgen05 tile, so
+// this stays a warp-level kernel; the 128-wide projections around it are the tcgen05 GEMMs in gemm_tc.cu.
+#include "kernels.cuh"
+
+namespace tpc {
+
+namespace {
+
+constexpr int KS = 132;  // smem row stride in floats (128 + 4): conflict-free fragment loads
+constexpr float BIG_NUMBER = 1e9f;
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t fbits(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ uint32_t tfbits(float x) { return __float_as_uint(tf32_rn(x)); }
+
+// stage `cols128` (128 floats at column offset col0 of a [rows][ld] matrix) of L rows into smem [Lp][KS]
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int ld, int col0, int L, int Lp, float* dst) {
+  for (int idx = threadIdx.x; idx < Lp * 32; idx += blockDim.x) {
+    const int r = idx >> 5, c4 = idx & 31;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < L) v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + col0 + c4 * 4);
+    *reinterpret_cast<float4*>(dst + r * KS + c4 * 4) = v;
+  }
+}
+
+// A fragment (16 rows x 8 cols at column c0) of a global row-major matrix; rows clamped to L-1
+__device__ __forceinline__ void load_a_frag(const float* __restrict__ base, int ld, int r0, int L, int c0, int g, int t,
+                                            float scale, uint32_t (&a)[4]) {
+  const int ra = min(r0 + g, L - 1), rb = min(r0 + g + 8, L - 1);
+  a[0] = fbits(base[(size_t)ra * ld + c0 + t] * scale);
+  a[1] = fbits(base[(size_t)rb * ld + c0 + t] * scale);
+  a[2] = fbits(base[(size_t)ra * ld + c0 + t + 4] * scale);
+  a[3] = fbits(base[(size_t)rb * ld + c0 + t + 4] * scale);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                       int mS, int m0, int L, float* __restrict__ att,
+                                                       float* __restrict__ lse) {
+  extern __shared__ float sm[];
+  const int ntiles = (L + 7) >> 3;
+  const int Lp = ntiles * 8;
+  float* Ks = sm;
+  float* Vs = Ks + Lp * KS;
+  float* Ms = Vs + Lp * KS;  // additive key mask: mask * -1e9, -inf beyond L
+  const int c = blockIdx.x;
+  const float* base = qkv + (size_t)c * L * 384;
+  stage_rows(base, 384, 128, L, Lp, Ks);
+  stage_rows(base, 384, 256, L, Lp, Vs);
+  for (int j = threadIdx.x; j < Lp; j += blockDim.x)
+    Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
+  __syncthreads();
+
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hc = h * 16;
+  for (int r0 = 0; r0 < L; r0 += 16) {
+    uint32_t qa[2][4];
+    load_a_frag(base, 384, r0, L, hc, g, t, 0.25f, qa[0]);      // 1/sqrt(depth=16), exact in fp32
+    load_a_frag(base, 384, r0, L, hc + 8, g, t, 0.25f, qa[1]);
+    float s[NT][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt < ntiles) {
+        const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
+        mma_tf32(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(kr[0]), fbits(kr[4]));
+        mma_tf32(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(kr[8]), fbits(kr[12]));
+        const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
+        s[nt][0] += ma; s[nt][1] += mb; s[nt][2] += ma; s[nt][3] += mb;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < ntiles) {
+        const float p0 = __expf(s[nt][0] - mx0), p1 = __expf(s[nt][1] - mx0);
+        const float p2 = __expf(s[nt][2] - mx1), p3 = __expf(s[nt][3] - mx1);
+        sum0 += p0 + p1;
+        sum1 += p2 + p3;
+        // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed
+        const uint32_t a0 = tfbits(p0), a1 = tfbits(p2), a2 = tfbits(p1), a3 = tfbits(p3);
+        const float* v0 = Vs + (nt * 8 + 2 * t) * KS + hc + g;
+        mma_tf32(o[0], a0, a1, a2, a3, fbits(v0[0]), fbits(v0[KS]));
+        mma_tf32(o[1], a0, a1, a2, a3, fbits(v0[8]), fbits(v0[KS + 8]));
+      }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float i0 = 1.f / sum0, i1 = 1.f / sum1;
+    const int ra = r0 + g, rb = r0 + g + 8;
+    if (ra < L) {
+      float* dst = att + ((size_t)c * L + ra) * 128 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(o[0][0] * i0), tf32_rn(o[0][1] * i0));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(o[1][0] * i0), tf32_rn(o[1][1] * i0));
+      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 + __logf(sum0);
+    }
+    if (rb < L) {
+      float* dst = att + ((size_t)c * L + rb) * 128 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(o[0][2] * i1), tf32_rn(o[0][3] * i1));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(o[1][2] * i1), tf32_rn(o[1][3] * i1));
+      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 + __logf(sum1);
+    }
+  }
+}
+
+// Backward. Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved
+// log-sum-exp; D_i = sum_d dO[i][d] * O[i][d] per head.
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
+                                                       const float* __restrict__ lse, const float* __restrict__ datt,
+                                                       const float* __restrict__ mask, int mS, int m0, int L,
+                                                       float* __restrict__ dqkv) {
+  extern __shared__ float sm[];
+  const int ntiles = (L + 7) >> 3;
+  const int Lp = ntiles * 8;
+  float* A_s = sm;                 // phase A: K   | phase B: Q
+  float* B_s = A_s + Lp * KS;      // phase A: V   | phase B: dO
+  float* Ms = B_s + Lp * KS;       // [Lp]
+  float* Ls = Ms + Lp;             // [8][Lp] log-sum-exp
+  float* Ds = Ls + 8 * Lp;         // [8][Lp]
+  const int c = blockIdx.x;
+  const float* base = qkv + (size_t)c * L * 384;
+  const float* obase = att + (size_t)c * L * 128;
+  const float* dobase = datt + (size_t)c * L * 128;
+  float* dbase = dqkv + (size_t)c * L * 384;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hc = h * 16;
+
+  stage_rows(base, 384, 128, L, Lp, A_s);
+  stage_rows(base, 384, 256, L, Lp, B_s);
+  for (int j = threadIdx.x; j < Lp; j += blockDim.x)
+    Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
+  for (int i = lane; i < Lp; i += 32) {
+    float d = 0.f, l = 0.f;
+    if (i < L) {
+      const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hc);
+      const float4* dp = reinterpret_cast<const float4*>(dobase + (size_t)i * 128 + hc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = op[q], b = dp[q];
+        d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
+      }
+      l = lse[((size_t)c * L + i) * 8 + h];
+    }
+    Ds[h * Lp + i] = d;
+    Ls[h * Lp + i] = l;
+  }
+  __syncthreads();
+
+  // ---------------- phase A: dQ ----------------
+  for (int r0 = 0; r0 < L; r0 += 16) {
+    uint32_t qa[2][4], da[2][4];
+    load_a_frag(base, 384, r0, L, hc, g, t, 0.25f, qa[0]);
+    load_a_frag(base, 384, r0, L, hc + 8, g, t, 0.25f, qa[1]);
+    load_a_frag(dobase, 128, r0, L, hc, g, t, 1.f, da[0]);
+    load_a_frag(dobase, 128, r0, L, hc + 8, g, t, 1.f, da[1]);
+    const int ia = min(r0 + g, Lp - 1), ib = min(r0 + g + 8, Lp - 1);
+    const float la = Ls[h * Lp + ia], lb = Ls[h * Lp + ib];
+    const float Da = Ds[h * Lp + ia], Db = Ds[h * Lp + ib];
+    float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int nt = 0; nt < ntiles; ++nt) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* kr = A_s + (nt * 8 + g) * KS + hc + t;
+      const float* vr = B_s + (nt * 8 + g) * KS + hc + t;
+      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(kr[0]), fbits(kr[4]));
+      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(kr[8]), fbits(kr[12]));
+      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], fbits(vr[0]), fbits(vr[4]));
+      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], fbits(vr[8]), fbits(vr[12]));
+      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
+      const float p0 = __expf(s[0] + ma - la), p1 = __expf(s[1] + mb - la);
+      const float p2 = __expf(s[2] + ma - lb), p3 = __expf(s[3] + mb - lb);
+      const uint32_t a0 = tfbits(p0 * (dp[0] - Da)), a2 = tfbits(p1 * (dp[1] - Da));
+      const uint32_t a1 = tfbits(p2 * (dp[2] - Db)), a3 = tfbits(p3 * (dp[3] - Db));
+      const float* k0 = A_s + (nt * 8 + 2 * t) * KS + hc + g;
+      mma_tf32(dq[0], a0, a1, a2, a3, fbits(k0[0]), fbits(k0[KS]));
+      mma_tf32(dq[1], a0, a1, a2, a3, fbits(k0[8]), fbits(k0[KS + 8]));
+    }
+    const int ra = r0 + g, rb = r0 + g + 8;
+    if (ra < L) {
+      float* dst = dbase + (size_t)ra * 384 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dq[0][0] * 0.25f), tf32_rn(dq[0][1] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[1][0] * 0.25f), tf32_rn(dq[1][1] * 0.25f));
+    }
+    if (rb < L) {
+      float* dst = dbase + (size_t)rb * 384 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dq[0][2] * 0.25f), tf32_rn(dq[0][3] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[1][2] * 0.25f), tf32_rn(dq[1][3] * 0.25f));
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase B: dK, dV (rows of the tiles are KEYS, columns are QUERIES) ----------------
+  stage_rows(base, 384, 0, L, Lp, A_s);       // Q
+  stage_rows(dobase, 128, 0, L, Lp, B_s);     // dO
+  __syncthreads();
+  for (int j0 = 0; j0 < L; j0 += 16) {
+    uint32_t ka[2][4], va[2][4];
+    load_a_frag(base + 128, 384, j0, L, hc, g, t, 0.25f, ka[0]);
+    load_a_frag(base + 128, 384, j0, L, hc + 8, g, t, 0.25f, ka[1]);
+    load_a_frag(base + 256, 384, j0, L, hc, g, t, 1.f, va[0]);
+    load_a_frag(base + 256, 384, j0, L, hc + 8, g, t, 1.f, va[1]);
+    const int ja = j0 + g, jb = j0 + g + 8;
+    const float ma = ja < L ? Ms[ja] : -INFINITY, mb = jb < L ? Ms[jb] : -INFINITY;
+    float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int it = 0; it < ntiles; ++it) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* qr = A_s + (it * 8 + g) * KS + hc + t;
+      const float* dr = B_s + (it * 8 + g) * KS + hc + t;
+      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], fbits(qr[0]), fbits(qr[4]));
+      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], fbits(qr[8]), fbits(qr[12]));
+      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], fbits(dr[0]), fbits(dr[4]));
+      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], fbits(dr[8]), fbits(dr[12]));
+      const int i0 = it * 8 + 2 * t, i1 = i0 + 1;   // query columns of this thread
+      const bool v0 = i0 < L, v1 = i1 < L;
+      const float l0 = Ls[h * Lp + i0], l1 = Ls[h * Lp + i1];
+      const float D0 = Ds[h * Lp + i0], D1 = Ds[h * Lp + i1];
+      const float p0 = v0 ? __expf(s[0] + ma - l0) : 0.f, p1 = v1 ? __expf(s[1] + ma - l1) : 0.f;
+      const float p2 = v0 ? __expf(s[2] + mb - l0) : 0.f, p3 = v1 ? __expf(s[3] + mb - l1) : 0.f;
+      const uint32_t pa0 = tfbits(p0), pa2 = tfbits(p1), pa1 = tfbits(p2), pa3 = tfbits(p3);
+      const uint32_t sa0 = tfbits(p0 * (dp[0] - D0)), sa2 = tfbits(p1 * (dp[1] - D1));
+      const uint32_t sa1 = tfbits(p2 * (dp[2] - D0)), sa3 = tfbits(p3 * (dp[3] - D1));
+      const float* d0 = B_s + (it * 8 + 2 * t) * KS + hc + g;
+      const float* q0 = A_s + (it * 8 + 2 * t) * KS + hc + g;
+      mma_tf32(dv[0], pa0, pa1, pa2, pa3, fbits(d0[0]), fbits(d0[KS]));
+      mma_tf32(dv[1], pa0, pa1, pa2, pa3, fbits(d0[8]), fbits(d0[KS + 8]));
+      mma_tf32(dk[0], sa0, sa1, sa2, sa3, fbits(q0[0]), fbits(q0[KS]));
+      mma_tf32(dk[1], sa0, sa1, sa2, sa3, fbits(q0[8]), fbits(q0[KS + 8]));
+    }
+    if (ja < L) {
+      float* dst = dbase + (size_t)ja * 384 + 128 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * 0.25f), tf32_rn(dk[0][1] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * 0.25f), tf32_rn(dk[1][1] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][0]), tf32_rn(dv[0][1]));
+      *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][0]), tf32_rn(dv[1][1]));
+    }
+    if (jb < L) {
+      float* dst = dbase + (size_t)jb * 384 + 128 + hc + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * 0.25f), tf32_rn(dk[0][3] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * 0.25f), tf32_rn(dk[1][3] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][2]), tf32_rn(dv[0][3]));
+      *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][2]), tf32_rn(dv[1][3]));
+    }
+  }
+}
+
+template <int NT>
+int launch_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
+               cudaStream_t st) {
+  const int Lp = ((L + 7) / 8) * 8;
+  const size_t smem = (size_t)(2 * Lp * KS + Lp) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attn_fwd_kernel<NT><<<C, 256, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+}  // namespace
+
+int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
+                  cudaStream_t st) {
+  if (C <= 0) return TPC_OK;
+  if (L < 1 || L > 208) return TPC_ERR_SHAPE;
+  if (L <= 64) return launch_fwd<8>(qkv, mask, mS, m0, C, L, att, lse, st);
+  if (L <= 104) return launch_fwd<13>(qkv, mask, mS, m0, C, L, att, lse, st);
+  if (L <= 160) return launch_fwd<20>(qkv, mask, mS, m0, C, L, att, lse, st);
+  return launch_fwd<26>(qkv, mask, mS, m0, C, L, att, lse, st);
+}
+
+int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
+                  int m0, int C, int L, float* dqkv, cudaStream_t st) {
+  if (C <= 0) return TPC_OK;
+  if (L < 1 || L > 200) return TPC_ERR_SHAPE;
+  const int Lp = ((L + 7) / 8) * 8;
+  const size_t smem = (size_t)(2 * Lp * KS + 17 * Lp) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attn_bwd_kernel<<<C, 256, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+}  // namespace tpc

@@ -6,12 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define TPC_OK 0
-#define TPC_ERR_CUDA -1
-#define TPC_ERR_ARG -2
-#define TPC_ERR_SHAPE -3
-#define TPC_ERR_WORKSPACE -4
-#define TPC_ERR_DRIVER -5
+#include "tpc.h"
 
 #define TPC_CHECK_CUDA(expr)                                                          \
   do {                                                                                \

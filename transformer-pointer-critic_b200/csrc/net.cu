@@ -1,0 +1,633 @@
+// Host-side orchestration of the actor / critic forward and backward passes, the T-step rollout and the A2C
+// gradient computation. Every arithmetic op is a kernel from gemm_tc.cu / attention.cu / kernels_simt.cu / env.cu;
+// this file only sequences launches on one stream and carves the caller-provided workspace.
+//
+// Reference call graph restated here:
+//   Encoder.call            common/encoder.py:67-99        -> encoder_forward / encoder_backward
+//   EncoderLayer.call       common/encoder_layer.py:15-23  -> enc_layer_forward / enc_layer_backward
+//   Decoder.call            actor/decoder.py:62-101        -> decoder_forward / decoder_backward
+//   CriticTransformer.call  critic/model.py:55-85          -> critic_forward / critic_backward
+//   trainer loop            agents/trainer.py:49-156       -> tpc_rollout / tpc_a2c_grads
+#include "model.cuh"
+#include "kernels.cuh"
+#include "env.cuh"
+
+using namespace tpc;
+
+namespace {
+
+struct Arena {
+  char* base = nullptr;
+  size_t size = 0, off = 0, peak = 0;
+  bool dry = false;
+  float* f(size_t nfloats) {
+    const size_t bytes = (nfloats * sizeof(float) + 1023) & ~size_t(1023);
+    char* p = base + off;
+    off += bytes;
+    if (off > peak) peak = off;
+    return reinterpret_cast<float*>(p);
+  }
+  bool fits() const { return dry || peak <= size; }
+};
+
+struct Ctx {
+  tpc_model* m;
+  const NetLayout* L;
+  const float* P;   // canonical parameters
+  const float* W;   // weight image
+  float* G;         // canonical gradient accumulator (nullptr in forward-only calls)
+  Arena* ar;
+  cudaStream_t st;
+  bool dry() const { return ar->dry; }
+  TmapCache* tc() const { return m->h->tmaps; }
+  int sms() const { return m->h->num_sms; }
+};
+
+struct MaskRef { const float* mask; int mS; int m0; };  // mask[c * mS + m0 + j]
+
+struct EncLayerActs { float *qkv, *lse, *att, *out1, *rstd1, *h, *out2, *rstd2; };
+struct EncActs {
+  float *emb_b = nullptr, *emb_r = nullptr, *cat = nullptr;
+  std::vector<EncLayerActs> bins, res, joint;
+  float* enc_out = nullptr;
+};
+struct StateRef { const float* state; int ld; const float* extra; };  // (C,S,ld) [+ is_empty (C,S)]
+
+#define RUN(expr)                         \
+  do {                                    \
+    if (!cx.dry()) { TPC_TRY(expr); }     \
+  } while (0)
+
+int gemm(Ctx& cx, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+         const GemmEpi& e, int ks = 1) {
+  if (cx.dry()) return TPC_OK;
+  return launch_gemm(cx.tc(), A, lda, Bt, ldb, D, ldd, M, N, K, e, ks, cx.sms(), cx.st);
+}
+
+// dW (+ db) of a Dense layer whose output gradient is dY[M, Nout]; W canonical [Kin][Nout]
+int dense_grads(Ctx& cx, const float* X, int ldx, const float* dY, int ldy, int M, const DenseP& d) {
+  if (cx.dry()) return TPC_OK;
+  WgradDst dst;
+  const int nj = ceil_div(d.out, 128);
+  for (int j = 0; j < nj; ++j) { dst.ptr[j] = cx.G + d.w + j * 128; dst.ld[j] = d.out; }
+  TPC_TRY(launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, d.in, d.out, dst, cx.sms(), cx.st));
+  return colsum(dY, ldy, M, d.out, cx.G + d.b, cx.st);
+}
+
+// fused output gradient dY[M, 128 * n] feeding n Dense layers of 128 outputs each (q|k|v or k2|v2|W2)
+int fused_grads(Ctx& cx, const float* X, int ldx, const float* dY, int ldy, int M, const DenseP* const* ds, int n) {
+  if (cx.dry()) return TPC_OK;
+  WgradDst dst;
+  for (int j = 0; j < n; ++j) { dst.ptr[j] = cx.G + ds[j]->w; dst.ld[j] = 128; }
+  TPC_TRY(launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, 128, 128 * n, dst, cx.sms(), cx.st));
+  for (int j = 0; j < n; ++j) TPC_TRY(colsum(dY + j * 128, ldy, M, 128, cx.G + ds[j]->b, cx.st));
+  return TPC_OK;
+}
+
+GemmEpi epi_bias(const float* b) { GemmEpi e; e.bias = b; return e; }
+GemmEpi epi_ln(const Ctx& cx, const float* b, const float* resid, const LnP& ln, float* rstd) {
+  GemmEpi e;
+  e.bias = b; e.aux = resid; e.ldaux = 128; e.aux_mode = 1; e.ln = 1;
+  e.gamma = cx.P + ln.g; e.beta = cx.P + ln.b; e.rstd_out = rstd;
+  return e;
+}
+GemmEpi epi_add(const float* aux, int ld) { GemmEpi e; e.aux = aux; e.ldaux = ld; e.aux_mode = 1; return e; }
+
+// ------------------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------------------
+void alloc_layer(Arena& ar, EncLayerActs& a, int rows, int dff) {
+  a.qkv = ar.f((size_t)rows * 384);
+  a.lse = ar.f((size_t)rows * 8);
+  a.att = ar.f((size_t)rows * 128);
+  a.out1 = ar.f((size_t)rows * 128);
+  a.rstd1 = ar.f(rows);
+  a.h = ar.f((size_t)rows * dff);
+  a.out2 = ar.f((size_t)rows * 128);
+  a.rstd2 = ar.f(rows);
+}
+
+int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int Lt, MaskRef mk, EncLayerActs& a) {
+  const int rows = C * Lt, dff = cx.L->dff;
+  alloc_layer(*cx.ar, a, rows, dff);
+  TPC_TRY(gemm(cx, x, 128, cx.W + lp.s.wqkv_t, 128, a.qkv, 384, rows, 384, 128, epi_bias(cx.W + lp.s.bqkv)));
+  RUN(attention_fwd(a.qkv, mk.mask, mk.mS, mk.m0, C, Lt, a.att, a.lse, cx.st));
+  TPC_TRY(gemm(cx, a.att, 128, cx.W + lp.s.wo_t, 128, a.out1, 128, rows, 128, 128,
+               epi_ln(cx, cx.P + lp.mha.o.b, x, lp.ln1, a.rstd1)));
+  GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
+  e1.relu = 1;
+  TPC_TRY(gemm(cx, a.out1, 128, cx.W + lp.s.w1_t, 128, a.h, dff, rows, dff, 128, e1));
+  TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w2_t, dff, a.out2, 128, rows, 128, dff,
+               epi_ln(cx, cx.P + lp.f2.b, a.out1, lp.ln2, a.rstd2)));
+  return TPC_OK;
+}
+
+struct BwdScratch { float *dA, *dB, *dQKV; };
+
+// dout: gradient w.r.t. out2, rows addressed through dmap; dx receives the gradient w.r.t. x
+int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int Lt, MaskRef mk, EncLayerActs& a,
+                       const float* dout, RowMap dmap, float* dx, BwdScratch& s) {
+  const int rows = C * Lt, dff = cx.L->dff;
+  const RowMap ident{Lt, Lt, 0};
+  RUN(ln_bwd(dout, dmap, a.out2, a.rstd2, cx.P + lp.ln2.g, cx.P + lp.ln2.b, rows, s.dA, cx.G + lp.ln2.g,
+             cx.G + lp.ln2.b, cx.st));
+  TPC_TRY(dense_grads(cx, a.h, dff, s.dA, 128, rows, lp.f2));
+  {  // dH = (dpre2 @ W2^T) * (h > 0), in place over h
+    GemmEpi e;
+    e.aux = a.h; e.ldaux = dff; e.aux_mode = 2;
+    TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.w2_c, 128, a.h, dff, rows, dff, 128, e));
+  }
+  TPC_TRY(dense_grads(cx, a.out1, 128, a.h, dff, rows, lp.f1));
+  TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w1_c, dff, s.dB, 128, rows, 128, dff, epi_add(s.dA, 128)));  // dout1
+  RUN(ln_bwd(s.dB, ident, a.out1, a.rstd1, cx.P + lp.ln1.g, cx.P + lp.ln1.b, rows, s.dA, cx.G + lp.ln1.g,
+             cx.G + lp.ln1.b, cx.st));
+  TPC_TRY(dense_grads(cx, a.att, 128, s.dA, 128, rows, lp.mha.o));
+  TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.wo_c, 128, s.dB, 128, rows, 128, 128, GemmEpi()));          // datt
+  RUN(attention_bwd(a.qkv, a.att, a.lse, s.dB, mk.mask, mk.mS, mk.m0, C, Lt, s.dQKV, cx.st));
+  const DenseP* qkv[3] = {&lp.mha.q, &lp.mha.k, &lp.mha.v};
+  TPC_TRY(fused_grads(cx, x, 128, s.dQKV, 384, rows, qkv, 3));
+  TPC_TRY(gemm(cx, s.dQKV, 384, cx.W + lp.s.wqkv_c, 384, dx, 128, rows, 128, 384, epi_add(s.dA, 128)));  // dx
+  return TPC_OK;
+}
+
+int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a) {
+  const NetLayout& L = *cx.L;
+  const int S = N + R, nl = L.nl;
+  Arena& ar = *cx.ar;
+  a.emb_b = ar.f((size_t)C * N * 128);
+  a.emb_r = ar.f((size_t)C * R * 128);
+  const DenseP& eb = L.enc.emb1;
+  const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
+  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, cx.P + eb.w, cx.P + eb.b, eb.in, a.emb_b, cx.st));
+  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * R, RowMap{R, S, N}, cx.P + er.w, cx.P + er.b, er.in, a.emb_r, cx.st));
+  a.bins.resize(nl); a.res.resize(nl); a.joint.resize(nl);
+  const float* xb = a.emb_b;
+  for (int i = 0; i < nl; ++i) {
+    TPC_TRY(enc_layer_forward(cx, L.enc.bins[i], xb, C, N, MaskRef{mha_mask, S, 0}, a.bins[i]));
+    xb = a.bins[i].out2;
+  }
+  const float* xr = a.emb_r;
+  for (int i = 0; i < nl; ++i) {
+    TPC_TRY(enc_layer_forward(cx, L.enc.res[i], xr, C, R, MaskRef{mha_mask, S, N}, a.res[i]));
+    xr = a.res[i].out2;
+  }
+  a.cat = ar.f((size_t)C * S * 128);
+  RUN(scatter_rows(xb, C * N, RowMap{N, S, 0}, a.cat, cx.st));
+  RUN(scatter_rows(xr, C * R, RowMap{R, S, N}, a.cat, cx.st));
+  const float* xj = a.cat;
+  for (int i = 0; i < nl; ++i) {
+    TPC_TRY(enc_layer_forward(cx, L.enc.joint[i], xj, C, S, MaskRef{mha_mask, S, 0}, a.joint[i]));
+    xj = a.joint[i].out2;
+  }
+  a.enc_out = const_cast<float*>(xj);
+  return TPC_OK;
+}
+
+// d_enc: gradient w.r.t. the encoder output [C*S,128] (overwritten as scratch)
+int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a, float* d_enc) {
+  const NetLayout& L = *cx.L;
+  const int S = N + R, nl = L.nl;
+  Arena& ar = *cx.ar;
+  BwdScratch s;
+  s.dA = ar.f((size_t)C * S * 128);
+  s.dB = ar.f((size_t)C * S * 128);
+  s.dQKV = ar.f((size_t)C * S * 384);
+  float* dx0 = ar.f((size_t)C * S * 128);
+  float* dx1 = ar.f((size_t)C * S * 128);
+  const float* dcur = d_enc;
+  float* dnext = dx0;
+  for (int i = nl - 1; i >= 0; --i) {
+    const float* x = i == 0 ? a.cat : a.joint[i - 1].out2;
+    TPC_TRY(enc_layer_backward(cx, L.enc.joint[i], x, C, S, MaskRef{mha_mask, S, 0}, a.joint[i], dcur,
+                               RowMap{S, S, 0}, dnext, s));
+    dcur = dnext;
+    dnext = (dnext == dx0) ? dx1 : dx0;
+  }
+  const float* dcat = dcur;          // [C*S,128]
+  float* other = dnext;              // free ping-pong buffer
+  float* third = const_cast<float*>(d_enc);  // d_enc is consumed: reuse as a third buffer
+  // bins stack
+  {
+    const float* dc = dcat;
+    RowMap dm{N, S, 0};
+    float* bufs[2] = {other, third};
+    int bi = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const float* x = i == 0 ? a.emb_b : a.bins[i - 1].out2;
+      TPC_TRY(enc_layer_backward(cx, L.enc.bins[i], x, C, N, MaskRef{mha_mask, S, 0}, a.bins[i], dc, dm, bufs[bi], s));
+      dc = bufs[bi];
+      dm = RowMap{N, N, 0};
+      bi ^= 1;
+    }
+    const DenseP& eb = L.enc.emb1;
+    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, dc, eb.in, cx.G + eb.w, cx.G + eb.b, cx.st));
+  }
+  // resources stack
+  {
+    const float* dc = dcat;
+    RowMap dm{R, S, N};
+    float* bufs[2] = {other, third};
+    int bi = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const float* x = i == 0 ? a.emb_r : a.res[i - 1].out2;
+      TPC_TRY(enc_layer_backward(cx, L.enc.res[i], x, C, R, MaskRef{mha_mask, S, N}, a.res[i], dc, dm, bufs[bi], s));
+      dc = bufs[bi];
+      dm = RowMap{R, R, 0};
+      bi ^= 1;
+    }
+    const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
+    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * R, RowMap{R, S, N}, dc, er.in, cx.G + er.w, cx.G + er.b, cx.st));
+  }
+  return TPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// actor decoder + pointer
+// ------------------------------------------------------------------------------------------------------
+struct DecLayerActs { float *v1, *o1, *rstd1, *q2, *kvw, *pc, *ctx, *o2, *rstd2, *f, *o3, *rstd3; };
+struct ActorActs {
+  EncActs enc;
+  float* y0 = nullptr;
+  std::vector<DecLayerActs> dec;
+  float *w1d = nullptr, *score = nullptr;
+};
+
+int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C, int S,
+                    ActorActs& a, float* logits, float* probs, int32_t* argmax) {
+  const NetLayout& L = *cx.L;
+  Arena& ar = *cx.ar;
+  const int dff = L.dff, nl = L.nl;
+  a.y0 = ar.f((size_t)C * 128);
+  RUN(small_dense_fwd(dec_input, L.demb.in, nullptr, C, RowMap{1, 1, 0}, cx.P + L.demb.w, cx.P + L.demb.b, L.demb.in,
+                      a.y0, cx.st));
+  a.dec.resize(nl);
+  const float* y = a.y0;
+  for (int i = 0; i < nl; ++i) {
+    const DecLayerP& lp = L.dec[i];
+    DecLayerActs& d = a.dec[i];
+    d.v1 = ar.f((size_t)C * 128); d.o1 = ar.f((size_t)C * 128); d.rstd1 = ar.f(C);
+    d.q2 = ar.f((size_t)C * 128); d.kvw = ar.f((size_t)C * S * 384); d.pc = ar.f((size_t)C * 8 * S);
+    d.ctx = ar.f((size_t)C * 128); d.o2 = ar.f((size_t)C * 128); d.rstd2 = ar.f(C);
+    d.f = ar.f((size_t)C * dff); d.o3 = ar.f((size_t)C * 128); d.rstd3 = ar.f(C);
+    // mha1 on a single token: softmax over one key == 1 => attn1 = dense(wv(y)) (actor/decoder_layer.py:22)
+    TPC_TRY(gemm(cx, y, 128, cx.W + lp.s.wv1_t, 128, d.v1, 128, C, 128, 128, epi_bias(cx.P + lp.mha1.v.b)));
+    TPC_TRY(gemm(cx, d.v1, 128, cx.W + lp.s.wo1_t, 128, d.o1, 128, C, 128, 128,
+                 epi_ln(cx, cx.P + lp.mha1.o.b, y, lp.ln1, d.rstd1)));
+    TPC_TRY(gemm(cx, d.o1, 128, cx.W + lp.s.wq2_t, 128, d.q2, 128, C, 128, 128, epi_bias(cx.P + lp.mha2.q.b)));
+    TPC_TRY(gemm(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
+                 epi_bias(cx.W + lp.s.bkvp)));
+    RUN(cross_attn_fwd(d.q2, d.kvw, mha_mask, C, S, d.ctx, d.pc, cx.st));
+    TPC_TRY(gemm(cx, d.ctx, 128, cx.W + lp.s.wo2_t, 128, d.o2, 128, C, 128, 128,
+                 epi_ln(cx, cx.P + lp.mha2.o.b, d.o1, lp.ln2, d.rstd2)));
+    GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
+    e1.relu = 1;
+    TPC_TRY(gemm(cx, d.o2, 128, cx.W + lp.s.w1_t, 128, d.f, dff, C, dff, 128, e1));
+    TPC_TRY(gemm(cx, d.f, dff, cx.W + lp.s.w2_t, dff, d.o3, 128, C, 128, dff,
+                 epi_ln(cx, cx.P + lp.f2.b, d.o2, lp.ln3, d.rstd3)));
+    y = d.o3;
+  }
+  a.w1d = ar.f((size_t)C * 128);
+  a.score = ar.f((size_t)C * S);
+  TPC_TRY(gemm(cx, y, 128, cx.W + L.w1p_t, 128, a.w1d, 128, C, 128, 128, epi_bias(cx.P + L.W1.b)));
+  RUN(pointer_fwd(a.w1d, a.dec[nl - 1].kvw, cx.P + L.V.w, cx.P + L.V.b, cx.m->dims.clip_C, cx.m->dims.has_clip, ptr_mask,
+                  C, S, a.score, logits, probs, argmax, cx.st));
+  return TPC_OK;
+}
+
+// dlogits [C,S] -> parameter gradients of the decoder; d_enc [C*S,128] receives the encoder-output gradient
+int decoder_backward(Ctx& cx, const float* dec_input, int C, int S, ActorActs& a, const float* dlogits, float* d_enc) {
+  const NetLayout& L = *cx.L;
+  Arena& ar = *cx.ar;
+  const int dff = L.dff, nl = L.nl;
+  float* dA = ar.f((size_t)C * 128);
+  float* dB = ar.f((size_t)C * 128);
+  float* dC = ar.f((size_t)C * 128);
+  float* dY = ar.f((size_t)C * 128);       // gradient w.r.t. the current layer's output o3
+  float* dq2 = ar.f((size_t)C * 128);
+  float* dw1d = ar.f((size_t)C * 128);
+  float* dkvw = ar.f((size_t)C * S * 384);
+  const RowMap id1{1, 1, 0};
+  DecLayerActs& last = a.dec[nl - 1];
+  if (!cx.dry()) TPC_CHECK_CUDA(cudaMemsetAsync(dkvw, 0, (size_t)C * S * 384 * sizeof(float), cx.st));
+  RUN(pointer_bwd(dlogits, a.score, a.w1d, last.kvw, cx.P + L.V.w, cx.m->dims.clip_C, cx.m->dims.has_clip, C, S, dw1d,
+                  dkvw, cx.G + L.V.w, cx.G + L.V.b, cx.st));
+  TPC_TRY(dense_grads(cx, last.o3, 128, dw1d, 128, C, L.W1));
+  TPC_TRY(gemm(cx, dw1d, 128, cx.W + L.w1p_c, 128, dY, 128, C, 128, 128, GemmEpi()));
+  bool enc_written = false;
+  for (int i = nl - 1; i >= 0; --i) {
+    const DecLayerP& lp = L.dec[i];
+    DecLayerActs& d = a.dec[i];
+    const float* y = i == 0 ? a.y0 : a.dec[i - 1].o3;
+    RUN(ln_bwd(dY, id1, d.o3, d.rstd3, cx.P + lp.ln3.g, cx.P + lp.ln3.b, C, dA, cx.G + lp.ln3.g, cx.G + lp.ln3.b, cx.st));
+    TPC_TRY(dense_grads(cx, d.f, dff, dA, 128, C, lp.f2));
+    {
+      GemmEpi e;
+      e.aux = d.f; e.ldaux = dff; e.aux_mode = 2;
+      TPC_TRY(gemm(cx, dA, 128, cx.W + lp.s.w2_c, 128, d.f, dff, C, dff, 128, e));
+    }
+    TPC_TRY(dense_grads(cx, d.o2, 128, d.f, dff, C, lp.f1));
+    TPC_TRY(gemm(cx, d.f, dff, cx.W + lp.s.w1_c, dff, dB, 128, C, 128, dff, epi_add(dA, 128)));        // do2
+    RUN(ln_bwd(dB, id1, d.o2, d.rstd2, cx.P + lp.ln2.g, cx.P + lp.ln2.b, C, dA, cx.G + lp.ln2.g, cx.G + lp.ln2.b, cx.st));
+    TPC_TRY(dense_grads(cx, d.ctx, 128, dA, 128, C, lp.mha2.o));
+    TPC_TRY(gemm(cx, dA, 128, cx.W + lp.s.wo2_c, 128, dC, 128, C, 128, 128, GemmEpi()));               // dctx
+    if (i != nl - 1 && !cx.dry()) TPC_CHECK_CUDA(cudaMemsetAsync(dkvw, 0, (size_t)C * S * 384 * sizeof(float), cx.st));
+    RUN(cross_attn_bwd(dC, d.q2, d.kvw, d.pc, C, S, dq2, dkvw, cx.st));
+    TPC_TRY(dense_grads(cx, d.o1, 128, dq2, 128, C, lp.mha2.q));
+    TPC_TRY(gemm(cx, dq2, 128, cx.W + lp.s.wq2_c, 128, dB, 128, C, 128, 128, epi_add(dA, 128)));       // do1
+    RUN(ln_bwd(dB, id1, d.o1, d.rstd1, cx.P + lp.ln1.g, cx.P + lp.ln1.b, C, dA, cx.G + lp.ln1.g, cx.G + lp.ln1.b, cx.st));
+    TPC_TRY(dense_grads(cx, d.v1, 128, dA, 128, C, lp.mha1.o));
+    TPC_TRY(gemm(cx, dA, 128, cx.W + lp.s.wo1_c, 128, dC, 128, C, 128, 128, GemmEpi()));               // dv1
+    TPC_TRY(dense_grads(cx, y, 128, dC, 128, C, lp.mha1.v));
+    TPC_TRY(gemm(cx, dC, 128, cx.W + lp.s.wv1_c, 128, dY, 128, C, 128, 128, epi_add(dA, 128)));        // dy
+    // encoder-output gradient through [K2 | V2 | W2] and their weight gradients
+    const int nf = (i == nl - 1) ? 3 : 2;
+    const DenseP* kvp[3] = {&lp.mha2.k, &lp.mha2.v, &L.W2};
+    TPC_TRY(fused_grads(cx, a.enc.enc_out, 128, dkvw, 384, C * S, kvp, nf));
+    TPC_TRY(gemm(cx, dkvw, 384, cx.W + lp.s.wkvp_c, 384, d_enc, 128, C * S, 128, 128 * nf,
+                 enc_written ? epi_add(d_enc, 128) : GemmEpi()));
+    enc_written = true;
+  }
+  RUN(small_dense_bwd(dec_input, L.demb.in, nullptr, C, id1, dY, L.demb.in, cx.G + L.demb.w, cx.G + L.demb.b, cx.st));
+  return TPC_OK;
+}
+
+int actor_forward(Ctx& cx, StateRef sr, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C,
+                  int N, int R, ActorActs& a, float* logits, float* probs, int32_t* argmax) {
+  TPC_TRY(encoder_forward(cx, sr, mha_mask, C, N, R, a.enc));
+  return decoder_forward(cx, dec_input, ptr_mask, mha_mask, C, N + R, a, logits, probs, argmax);
+}
+
+int actor_backward(Ctx& cx, StateRef sr, const float* dec_input, const float* mha_mask, int C, int N, int R,
+                   ActorActs& a, const float* dlogits) {
+  float* d_enc = cx.ar->f((size_t)C * (N + R) * 128);
+  TPC_TRY(decoder_backward(cx, dec_input, C, N + R, a, dlogits, d_enc));
+  return encoder_backward(cx, sr, mha_mask, C, N, R, a.enc, d_enc);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// critic
+// ------------------------------------------------------------------------------------------------------
+struct CriticActs { EncActs enc; float *h0 = nullptr, *h1 = nullptr; };
+
+int critic_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, CriticActs& a, float* values) {
+  const NetLayout& L = *cx.L;
+  const int S = N + R;
+  if (S != L.S_critic) {
+    fprintf(stderr, "[tpc] critic is tied to the training shape S=%d (critic/model.py:65), got S=%d\n", L.S_critic, S);
+    return TPC_ERR_SHAPE;
+  }
+  TPC_TRY(encoder_forward(cx, sr, mha_mask, C, N, R, a.enc));
+  a.h0 = cx.ar->f((size_t)C * 128);
+  a.h1 = cx.ar->f((size_t)C * 128);
+  const int K = S * 128;
+  RUN(fill_rows_bias(a.h0, cx.P + L.h0.b, C, cx.st));
+  GemmEpi e;
+  e.atomic = 1; e.round_out = 0;
+  int ks = ceil_div(cx.sms(), ceil_div(C, 128));
+  if (ks > K / 32 / 4) ks = K / 32 / 4;
+  if (ks < 1) ks = 1;
+  TPC_TRY(gemm(cx, a.enc.enc_out, K, cx.W + L.h0_t, K, a.h0, 128, C, 128, K, e, ks));   // Flatten -> Dense(128)
+  RUN(round_tf32_inplace(a.h0, (size_t)C * 128, cx.st));
+  TPC_TRY(gemm(cx, a.h0, 128, cx.W + L.h1_t, 128, a.h1, 128, C, 128, 128, epi_bias(cx.P + L.h1.b)));
+  RUN(value_head_fwd(a.h1, cx.P + L.hv.w, cx.P + L.hv.b, C, values, cx.st));
+  return TPC_OK;
+}
+
+int critic_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, CriticActs& a, const float* dv) {
+  const NetLayout& L = *cx.L;
+  const int S = N + R, K = S * 128;
+  Arena& ar = *cx.ar;
+  float* dh1 = ar.f((size_t)C * 128);
+  float* dh0 = ar.f((size_t)C * 128);
+  float* d_enc = ar.f((size_t)C * S * 128);
+  RUN(value_head_bwd(dv, a.h1, cx.P + L.hv.w, C, dh1, cx.G + L.hv.w, cx.G + L.hv.b, cx.st));
+  TPC_TRY(dense_grads(cx, a.h0, 128, dh1, 128, C, L.h1));
+  TPC_TRY(gemm(cx, dh1, 128, cx.W + L.h1_c, 128, dh0, 128, C, 128, 128, GemmEpi()));
+  TPC_TRY(dense_grads(cx, a.enc.enc_out, K, dh0, 128, C, L.h0));
+  TPC_TRY(gemm(cx, dh0, 128, cx.W + L.h0_c, 128, d_enc, K, C, K, 128, GemmEpi()));
+  return encoder_backward(cx, sr, mha_mask, C, N, R, a.enc, d_enc);
+}
+
+__global__ void gather_dec_kernel(const float* __restrict__ batch, int B, int S, int F, int tok, float* __restrict__ dec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * F) return;
+  const int b = i / F, f = i % F;
+  dec[i] = batch[((size_t)b * S + tok) * F + f];
+}
+
+__global__ void scatter_reward_kernel(const float* __restrict__ r, int B, int T, int t, float* __restrict__ rewards) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) rewards[(size_t)b * T + t] = r[b];
+}
+
+Ctx make_ctx(tpc_model* m, int which, const float* params, const float* shadow, float* grads, Arena* ar, void* stream) {
+  Ctx cx;
+  cx.m = m;
+  cx.L = which ? &m->critic : &m->actor;
+  cx.P = params; cx.W = shadow; cx.G = grads; cx.ar = ar; cx.st = (cudaStream_t)stream;
+  return cx;
+}
+
+int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_params, const float* critic_shadow,
+                   const float* critic_params, const tpc_rollout_buffers* buf, int B, int N, int R,
+                   const tpc_a2c_hyper* hp, float* actor_grads, float* critic_grads, float* values, float* advantages,
+                   float* losses, Arena& ar, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = N + R, T = R, F = m->cfg.dec_features;
+  const long long n = (long long)T * B;
+  int chunk = hp->chunk_states > 0 ? hp->chunk_states : 2048;
+  if (chunk > n) chunk = (int)n;
+  const float inv_total = 1.0f / (float)(hp->total_states > 0 ? hp->total_states : n);
+  float* Rt = ar.f((size_t)n);
+  float* dv = ar.f((size_t)chunk);
+  float* dlogits = ar.f((size_t)chunk * S);
+  float* logits = ar.f((size_t)chunk * S);
+  const size_t mark = ar.off;
+  if (!ar.dry) TPC_TRY(discounted_returns(buf->rewards, B, T, hp->gamma, Rt, st));
+  const bool cost = buf->is_empties != nullptr;
+  // ---- critic: value loss + gradients (agents/agent.py:126-166, trainer.py:115-123)
+  for (long long s0 = 0; s0 < n; s0 += chunk) {
+    const int C = (int)((n - s0) < chunk ? (n - s0) : chunk);
+    ar.off = mark;
+    Ctx cx = make_ctx(m, 1, critic_params, critic_shadow, critic_grads, &ar, stream);
+    StateRef sr{buf->states + (size_t)s0 * S * F, F, cost ? buf->is_empties + (size_t)s0 * S : nullptr};
+    const float* mha = buf->mha_masks + (size_t)s0 * S;
+    CriticActs a;
+    TPC_TRY(critic_forward(cx, sr, mha, C, N, R, a, values + s0));
+    RUN(critic_loss_bwd(Rt + s0, values + s0, C, hp->values_loss_coefficient, inv_total, advantages + s0, dv, losses, st));
+    TPC_TRY(critic_backward(cx, sr, mha, C, N, R, a, dv));
+    if (!ar.fits()) return TPC_ERR_WORKSPACE;
+    if (ar.dry) break;
+  }
+  // ---- actor: policy loss (+ zero-gradient entropy term) and gradients (agents/agent.py:168-242, trainer.py:125-141)
+  for (long long s0 = 0; s0 < n; s0 += chunk) {
+    const int C = (int)((n - s0) < chunk ? (n - s0) : chunk);
+    ar.off = mark;
+    Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, actor_grads, &ar, stream);
+    StateRef sr{buf->states + (size_t)s0 * S * F, F, cost ? buf->is_empties + (size_t)s0 * S : nullptr};
+    const float* mha = buf->mha_masks + (size_t)s0 * S;
+    const float* dec = buf->dec_inputs + (size_t)s0 * F;
+    ActorActs a;
+    TPC_TRY(actor_forward(cx, sr, dec, buf->ptr_masks + (size_t)s0 * S, mha, C, N, R, a, logits, nullptr, nullptr));
+    RUN(actor_loss_bwd(logits, buf->actions + s0, advantages + s0, C, S, hp->entropy_coefficient, inv_total, dlogits,
+                       losses, st));
+    TPC_TRY(actor_backward(cx, sr, dec, mha, C, N, R, a, dlogits));
+    if (!ar.fits()) return TPC_ERR_WORKSPACE;
+    if (ar.dry) break;
+  }
+  return TPC_OK;
+}
+
+int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
+                 const tpc_rollout_buffers* buf, int B, int N, int R, int greedy, uint64_t seed, int64_t id0,
+                 int64_t epoch, Arena& ar, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = N + R, T = R, F = e->num_features;
+  float* probs = ar.f((size_t)B * S);
+  int32_t* amax = reinterpret_cast<int32_t*>(ar.f(B));
+  float* rtmp = ar.f(B);
+  float* dec_tmp = ar.f((size_t)B * F);
+  float* mask_tmp = ar.f((size_t)B * S);
+  const size_t mark = ar.off;
+  for (int t = 0; t < T; ++t) {
+    ar.off = mark;
+    Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, stream);
+    float* dec = buf->dec_inputs ? buf->dec_inputs + (size_t)t * B * F : dec_tmp;
+    float* pmask = buf->ptr_masks ? buf->ptr_masks + (size_t)t * B * S : mask_tmp;
+    const float* mha = buf->mha_mask;
+    int32_t* act = buf->actions + (size_t)t * B;
+    if (!ar.dry) {
+      gather_dec_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(buf->batch, B, S, F, N + t, dec);
+      TPC_CHECK_LAUNCH();
+      // Agent.store copies (agents/trainer.py:68-76): state, mha mask (and is_empty) BEFORE the step
+      if (buf->states)
+        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->states + (size_t)t * B * S * F, buf->batch, (size_t)B * S * F * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+      if (buf->is_empties && buf->is_empty)
+        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->is_empties + (size_t)t * B * S, buf->is_empty, (size_t)B * S * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+      if (buf->mha_masks)
+        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->mha_masks + (size_t)t * B * S, buf->mha_mask, (size_t)B * S * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+      TPC_TRY(env_feasible_mask(*e, buf->batch, F, dec, buf->bin_net_mask, B, S, pmask, st));
+    }
+    ActorActs a;
+    StateRef sr{buf->batch, F, buf->is_empty};
+    TPC_TRY(actor_forward(cx, sr, dec, pmask, mha, B, N, R, a, buf->logits ? buf->logits + (size_t)t * B * S : nullptr,
+                          probs, greedy ? act : amax));
+    if (!ar.fits()) return TPC_ERR_WORKSPACE;
+    if (ar.dry) break;
+    if (!greedy) TPC_TRY(sample_categorical(probs, B, S, seed, id0, epoch * T + t, act, st));
+    TPC_TRY(env_step(*e, buf->batch, buf->bin_net_mask, nullptr, buf->mha_mask, buf->is_empty, act, N + t, B, N, R, rtmp,
+                     st));
+    scatter_reward_kernel<<<ceil_div(B, 256), 256, 0, st>>>(rtmp, B, T, t, buf->rewards);
+    TPC_CHECK_LAUNCH();
+  }
+  return TPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tpc_workspace_bytes(const tpc_model* mc, int mode, int nstates, int num_bins, int num_resources) {
+  tpc_model* m = const_cast<tpc_model*>(mc);
+  if (!m || nstates <= 0) return 0;
+  Arena ar;
+  ar.dry = true;
+  const int N = num_bins, R = num_resources, C = nstates;
+  int rc = TPC_OK;
+  if (mode == 0 || mode == 2) {
+    Ctx cx = make_ctx(m, 0, nullptr, nullptr, nullptr, &ar, nullptr);
+    ActorActs a;
+    rc = actor_forward(cx, StateRef{nullptr, 3, nullptr}, nullptr, nullptr, nullptr, C, N, R, a, nullptr, nullptr, nullptr);
+    if (rc == TPC_OK && mode == 2) rc = actor_backward(cx, StateRef{nullptr, 3, nullptr}, nullptr, nullptr, C, N, R, a, nullptr);
+  } else if (mode == 1 || mode == 3) {
+    Ctx cx = make_ctx(m, 1, nullptr, nullptr, nullptr, &ar, nullptr);
+    CriticActs a;
+    rc = critic_forward(cx, StateRef{nullptr, 3, nullptr}, nullptr, C, N, R, a, nullptr);
+    if (rc == TPC_OK && mode == 3) rc = critic_backward(cx, StateRef{nullptr, 3, nullptr}, nullptr, C, N, R, a, nullptr);
+  } else if (mode == 4) {   // rollout of nstates episodes
+    tpc_env_config e{};
+    e.num_features = m->cfg.dec_features;
+    tpc_rollout_buffers buf{};
+    rc = rollout_impl(m, &e, nullptr, nullptr, &buf, C, N, R, 1, 0, 0, 0, ar, nullptr);
+  }
+  if (rc != TPC_OK) return 0;
+  return ar.peak + 4096;
+}
+
+// workspace of tpc_a2c_grads for B episodes and the given chunk size
+size_t tpc_a2c_workspace_bytes(const tpc_model* mc, int B, int num_bins, int num_resources, int chunk_states) {
+  tpc_model* m = const_cast<tpc_model*>(mc);
+  if (!m) return 0;
+  Arena ar;
+  ar.dry = true;
+  tpc_a2c_hyper hp{};
+  hp.chunk_states = chunk_states;
+  tpc_rollout_buffers buf{};
+  int rc = a2c_grads_impl(m, nullptr, nullptr, nullptr, nullptr, &buf, B, num_bins, num_resources, &hp, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, ar, nullptr);
+  if (rc != TPC_OK) return 0;
+  const size_t mx = ar.peak;
+  return mx + 4096;
+}
+
+int tpc_actor_forward(tpc_model* m, const float* shadow, const float* params, const float* state,
+                      const float* dec_input, const float* ptr_mask, const float* mha_mask, int B, int num_bins,
+                      int num_resources, float* logits, float* probs, int32_t* argmax, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!m || !shadow || !params || !state || !dec_input || !ptr_mask || !mha_mask || !workspace) return TPC_ERR_ARG;
+  Arena ar;
+  ar.base = (char*)workspace; ar.size = workspace_bytes;
+  if (tpc_workspace_bytes(m, 0, B, num_bins, num_resources) > workspace_bytes) return TPC_ERR_WORKSPACE;
+  Ctx cx = make_ctx(m, 0, params, shadow, nullptr, &ar, stream);
+  ActorActs a;
+  const int ld = m->cfg.common_embedding ? m->cfg.dec_features : m->cfg.num_bin_features;
+  return actor_forward(cx, StateRef{state, ld, nullptr}, dec_input, ptr_mask, mha_mask, B, num_bins, num_resources, a,
+                       logits, probs, argmax);
+}
+
+int tpc_critic_forward(tpc_model* m, const float* shadow, const float* params, const float* state,
+                       const float* mha_mask, int nstates, int num_bins, int num_resources, float* values,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !shadow || !params || !state || !mha_mask || !values || !workspace) return TPC_ERR_ARG;
+  Arena ar;
+  ar.base = (char*)workspace; ar.size = workspace_bytes;
+  if (tpc_workspace_bytes(m, 1, nstates, num_bins, num_resources) > workspace_bytes) return TPC_ERR_WORKSPACE;
+  Ctx cx = make_ctx(m, 1, params, shadow, nullptr, &ar, stream);
+  CriticActs a;
+  const int ld = m->cfg.common_embedding ? m->cfg.dec_features : m->cfg.num_bin_features;
+  return critic_forward(cx, StateRef{state, ld, nullptr}, mha_mask, nstates, num_bins, num_resources, a, values);
+}
+
+int tpc_rollout(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
+                const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources, int greedy, uint64_t seed,
+                int64_t episode_id0, int64_t epoch, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !e || !actor_shadow || !actor_params || !buf || !workspace) return TPC_ERR_ARG;
+  if (!buf->batch || !buf->bin_net_mask || !buf->mha_mask || !buf->actions || !buf->rewards) return TPC_ERR_ARG;
+  if (e->num_features != m->cfg.dec_features) return TPC_ERR_SHAPE;
+  if (tpc_workspace_bytes(m, 4, B, num_bins, num_resources) > workspace_bytes) return TPC_ERR_WORKSPACE;
+  Arena ar;
+  ar.base = (char*)workspace; ar.size = workspace_bytes;
+  return rollout_impl(m, e, actor_shadow, actor_params, buf, B, num_bins, num_resources, greedy, seed, episode_id0,
+                      epoch, ar, stream);
+}
+
+int tpc_a2c_grads(tpc_model* m, const float* actor_shadow, const float* actor_params, const float* critic_shadow,
+                  const float* critic_params, const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources,
+                  const tpc_a2c_hyper* hp, float* actor_grads, float* critic_grads, float* values, float* advantages,
+                  float* losses, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !actor_shadow || !actor_params || !critic_shadow || !critic_params || !buf || !hp || !actor_grads ||
+      !critic_grads || !values || !advantages || !losses || !workspace)
+    return TPC_ERR_ARG;
+  if (!buf->states || !buf->dec_inputs || !buf->ptr_masks || !buf->mha_masks || !buf->actions || !buf->rewards)
+    return TPC_ERR_ARG;
+  if (tpc_a2c_workspace_bytes(m, B, num_bins, num_resources, hp->chunk_states) > workspace_bytes) return TPC_ERR_WORKSPACE;
+  Arena ar;
+  ar.base = (char*)workspace; ar.size = workspace_bytes;
+  return a2c_grads_impl(m, actor_shadow, actor_params, critic_shadow, critic_params, buf, B, num_bins, num_resources, hp,
+                        actor_grads, critic_grads, values, advantages, losses, ar, stream);
+}
+
+}  // extern "C"
