@@ -99,13 +99,15 @@ size_t tpc_a2c_workspace_bytes(const tpc_model* m, int B, int num_bins, int num_
  * stand-alone operators (unit-test granularity)
  * ---------------------------------------------------------------------------------------------------- */
 /* D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags bit0 relu, bit1 layernorm(gamma,beta -> rstd_out),
- * bit2 round outputs to TF32, bit3 atomic split-K accumulate; aux_mode 0 none / 1 add / 2 relu-gate */
+ * bit2 round outputs to TF32, bit3 atomic split-K accumulate; aux_mode 0 none / 1 add / 2 relu-gate.
+ * Bt_lo == NULL: one TF32 pass (operands truncated by the tensor core). Bt_lo = Bt - trunc_tf32(Bt): 3xTF32,
+ * fp32-accurate (the forward passes use this; the backward passes use one pass on TF32-rounded gradients). */
 int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
              const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
-             float* rstd_out, int flags, int k_splits, void* stream);
-/* dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout] */
-int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int M, int Kin,
-              int Nout, void* stream);
+             float* rstd_out, int flags, int k_splits, const float* Bt_lo, void* stream);
+/* dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout];  db[Nout] += colsum(dY) when db != NULL */
+int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int M,
+              int Kin, int Nout, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * model forward passes (step-wise, API-exact mode used by Agent.act / tests)

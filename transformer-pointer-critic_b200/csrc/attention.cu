@@ -45,8 +45,11 @@ __device__ __forceinline__ void load_a_frag(const float* __restrict__ base, int 
   a[3] = fbits(base[(size_t)rb * ld + c0 + t + 4] * scale);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+// Forward: 16 warps per state; head h is shared by warps h and h+8 (alternating 16-row query blocks).
+// Two passes over the keys keep the register footprint small: pass 1 finds the row maximum (plain TF32),
+// pass 2 recomputes the scores in 3xTF32 (hi/lo split of Q and K: fp32-level logits, the softmax amplifies
+// score errors), exponentiates and accumulates P.V (P, V rounded to nearest TF32).
+__global__ void __launch_bounds__(512) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                        int mS, int m0, int L, float* __restrict__ att,
                                                        float* __restrict__ lse) {
   extern __shared__ float sm[];
@@ -63,45 +66,73 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   __syncthreads();
 
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int h = warp & 7, sub = warp >> 3;
   const int hc = h * 16;
-  for (int r0 = 0; r0 < L; r0 += 16) {
-    uint32_t qa[2][4];
-    load_a_frag(base, 384, r0, L, hc, g, t, 0.25f, qa[0]);      // 1/sqrt(depth=16), exact in fp32
-    load_a_frag(base, 384, r0, L, hc + 8, g, t, 0.25f, qa[1]);
-    float s[NT][4];
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+  for (int r0 = sub * 16; r0 < L; r0 += 32) {
+    uint32_t qh[2][4], ql[2][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      if (nt < ntiles) {
-        const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
-        mma_tf32(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(kr[0]), fbits(kr[4]));
-        mma_tf32(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(kr[8]), fbits(kr[12]));
-        const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-        s[nt][0] += ma; s[nt][1] += mb; s[nt][2] += ma; s[nt][3] += mb;
-        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t raw[4];
+      load_a_frag(base, 384, r0, L, hc + kk * 8, g, t, 0.25f, raw);   // 1/sqrt(depth=16), exact in fp32
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = __uint_as_float(raw[i]);
+        const float hi = tf32_rn(x);
+        qh[kk][i] = __float_as_uint(hi);
+        ql[kk][i] = __float_as_uint(x - hi);
       }
+    }
+    // ---- pass 1: row maxima
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    for (int nt = 0; nt < ntiles; ++nt) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
+      mma_tf32(s, qh[0][0], qh[0][1], qh[0][2], qh[0][3], tfbits(kr[0]), tfbits(kr[4]));
+      mma_tf32(s, qh[1][0], qh[1][1], qh[1][2], qh[1][3], tfbits(kr[8]), tfbits(kr[12]));
+      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
+      mx0 = fmaxf(mx0, fmaxf(s[0] + ma, s[1] + mb));
+      mx1 = fmaxf(mx1, fmaxf(s[2] + ma, s[3] + mb));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    // ---- pass 2: exact scores, softmax numerators, P.V
     float sum0 = 0.f, sum1 = 0.f;
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
+    for (int nt = 0; nt < ntiles; ++nt) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      if (nt < ntiles) {
-        const float p0 = __expf(s[nt][0] - mx0), p1 = __expf(s[nt][1] - mx0);
-        const float p2 = __expf(s[nt][2] - mx1), p3 = __expf(s[nt][3] - mx1);
-        sum0 += p0 + p1;
-        sum1 += p2 + p3;
-        // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed
-        const uint32_t a0 = tfbits(p0), a1 = tfbits(p2), a2 = tfbits(p1), a3 = tfbits(p3);
-        const float* v0 = Vs + (nt * 8 + 2 * t) * KS + hc + g;
-        mma_tf32(o[0], a0, a1, a2, a3, fbits(v0[0]), fbits(v0[KS]));
-        mma_tf32(o[1], a0, a1, a2, a3, fbits(v0[8]), fbits(v0[KS + 8]));
+      for (int kk = 0; kk < 2; ++kk) {
+        const float k0 = kr[kk * 8], k1 = kr[kk * 8 + 4];
+        const float k0h = tf32_rn(k0), k1h = tf32_rn(k1);
+        const uint32_t b0h = __float_as_uint(k0h), b1h = __float_as_uint(k1h);
+        const uint32_t b0l = __float_as_uint(k0 - k0h), b1l = __float_as_uint(k1 - k1h);
+        mma_tf32(s, ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3], b0h, b1h);
+        mma_tf32(s, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], b0l, b1l);
+        mma_tf32(s, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], b0h, b1h);
+      }
+      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
+      const float p0 = __expf(s[0] + ma - mx0), p1 = __expf(s[1] + mb - mx0);
+      const float p2 = __expf(s[2] + ma - mx1), p3 = __expf(s[3] + mb - mx1);
+      sum0 += p0 + p1;
+      sum1 += p2 + p3;
+      // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
+      // 3xTF32 again: with few keys there is no averaging of the operand rounding.
+      const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
+      const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
+      const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
+      const float* v0 = Vs + (nt * 8 + 2 * t) * KS + hc + g;
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        const float va = v0[n2 * 8], vb = v0[KS + n2 * 8];
+        const float vah = tf32_rn(va), vbh = tf32_rn(vb);
+        mma_tf32(o[n2], l0, l1, l2, l3, fbits(vah), fbits(vbh));
+        mma_tf32(o[n2], a0, a1, a2, a3, fbits(va - vah), fbits(vb - vbh));
+        mma_tf32(o[n2], a0, a1, a2, a3, fbits(vah), fbits(vbh));
       }
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
@@ -112,22 +143,28 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
     const int ra = r0 + g, rb = r0 + g + 8;
     if (ra < L) {
       float* dst = att + ((size_t)c * L + ra) * 128 + hc + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(o[0][0] * i0), tf32_rn(o[0][1] * i0));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(o[1][0] * i0), tf32_rn(o[1][1] * i0));
-      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 + __logf(sum0);
+      *reinterpret_cast<float2*>(dst) = make_float2(o[0][0] * i0, o[0][1] * i0);
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][0] * i0, o[1][1] * i0);
+      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 + logf(sum0);
     }
     if (rb < L) {
       float* dst = att + ((size_t)c * L + rb) * 128 + hc + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(o[0][2] * i1), tf32_rn(o[0][3] * i1));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(o[1][2] * i1), tf32_rn(o[1][3] * i1));
-      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 + __logf(sum1);
+      *reinterpret_cast<float2*>(dst) = make_float2(o[0][2] * i1, o[0][3] * i1);
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][2] * i1, o[1][3] * i1);
+      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 + logf(sum1);
     }
   }
 }
 
-// Backward. Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved
+// Backward (plain TF32 with operands rounded to nearest on the fly). 16 warps: head h = warps h, h+8.
+// Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved
 // log-sum-exp; D_i = sum_d dO[i][d] * O[i][d] per head.
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
+__device__ __forceinline__ void round_frag(uint32_t (&a)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = tfbits(__uint_as_float(a[i]));
+}
+
+__global__ void __launch_bounds__(512) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
                                                        const float* __restrict__ lse, const float* __restrict__ datt,
                                                        const float* __restrict__ mask, int mS, int m0, int L,
                                                        float* __restrict__ dqkv) {
@@ -144,14 +181,15 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   const float* obase = att + (size_t)c * L * 128;
   const float* dobase = datt + (size_t)c * L * 128;
   float* dbase = dqkv + (size_t)c * L * 384;
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int h = warp & 7, sub = warp >> 3;
   const int hc = h * 16;
 
   stage_rows(base, 384, 128, L, Lp, A_s);
   stage_rows(base, 384, 256, L, Lp, B_s);
   for (int j = threadIdx.x; j < Lp; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
-  for (int i = lane; i < Lp; i += 32) {
+  for (int i = lane + 32 * sub; i < Lp; i += 64) {
     float d = 0.f, l = 0.f;
     if (i < L) {
       const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hc);
@@ -169,32 +207,34 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   __syncthreads();
 
   // ---------------- phase A: dQ ----------------
-  for (int r0 = 0; r0 < L; r0 += 16) {
+  for (int r0 = sub * 16; r0 < L; r0 += 32) {
     uint32_t qa[2][4], da[2][4];
     load_a_frag(base, 384, r0, L, hc, g, t, 0.25f, qa[0]);
     load_a_frag(base, 384, r0, L, hc + 8, g, t, 0.25f, qa[1]);
     load_a_frag(dobase, 128, r0, L, hc, g, t, 1.f, da[0]);
     load_a_frag(dobase, 128, r0, L, hc + 8, g, t, 1.f, da[1]);
+    round_frag(qa[0]); round_frag(qa[1]); round_frag(da[0]); round_frag(da[1]);
     const int ia = min(r0 + g, Lp - 1), ib = min(r0 + g + 8, Lp - 1);
     const float la = Ls[h * Lp + ia], lb = Ls[h * Lp + ib];
     const float Da = Ds[h * Lp + ia], Db = Ds[h * Lp + ib];
     float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
     for (int nt = 0; nt < ntiles; ++nt) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
       const float* kr = A_s + (nt * 8 + g) * KS + hc + t;
       const float* vr = B_s + (nt * 8 + g) * KS + hc + t;
-      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(kr[0]), fbits(kr[4]));
-      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(kr[8]), fbits(kr[12]));
-      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], fbits(vr[0]), fbits(vr[4]));
-      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], fbits(vr[8]), fbits(vr[12]));
+      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], tfbits(kr[0]), tfbits(kr[4]));
+      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], tfbits(kr[8]), tfbits(kr[12]));
+      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], tfbits(vr[0]), tfbits(vr[4]));
+      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], tfbits(vr[8]), tfbits(vr[12]));
       const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
       const float p0 = __expf(s[0] + ma - la), p1 = __expf(s[1] + mb - la);
       const float p2 = __expf(s[2] + ma - lb), p3 = __expf(s[3] + mb - lb);
       const uint32_t a0 = tfbits(p0 * (dp[0] - Da)), a2 = tfbits(p1 * (dp[1] - Da));
       const uint32_t a1 = tfbits(p2 * (dp[2] - Db)), a3 = tfbits(p3 * (dp[3] - Db));
       const float* k0 = A_s + (nt * 8 + 2 * t) * KS + hc + g;
-      mma_tf32(dq[0], a0, a1, a2, a3, fbits(k0[0]), fbits(k0[KS]));
-      mma_tf32(dq[1], a0, a1, a2, a3, fbits(k0[8]), fbits(k0[KS + 8]));
+      mma_tf32(dq[0], a0, a1, a2, a3, tfbits(k0[0]), tfbits(k0[KS]));
+      mma_tf32(dq[1], a0, a1, a2, a3, tfbits(k0[8]), tfbits(k0[KS + 8]));
     }
     const int ra = r0 + g, rb = r0 + g + 8;
     if (ra < L) {
@@ -214,24 +254,26 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   stage_rows(base, 384, 0, L, Lp, A_s);       // Q
   stage_rows(dobase, 128, 0, L, Lp, B_s);     // dO
   __syncthreads();
-  for (int j0 = 0; j0 < L; j0 += 16) {
+  for (int j0 = sub * 16; j0 < L; j0 += 32) {
     uint32_t ka[2][4], va[2][4];
     load_a_frag(base + 128, 384, j0, L, hc, g, t, 0.25f, ka[0]);
     load_a_frag(base + 128, 384, j0, L, hc + 8, g, t, 0.25f, ka[1]);
     load_a_frag(base + 256, 384, j0, L, hc, g, t, 1.f, va[0]);
     load_a_frag(base + 256, 384, j0, L, hc + 8, g, t, 1.f, va[1]);
+    round_frag(ka[0]); round_frag(ka[1]); round_frag(va[0]); round_frag(va[1]);
     const int ja = j0 + g, jb = j0 + g + 8;
     const float ma = ja < L ? Ms[ja] : -INFINITY, mb = jb < L ? Ms[jb] : -INFINITY;
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
     for (int it = 0; it < ntiles; ++it) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
       const float* qr = A_s + (it * 8 + g) * KS + hc + t;
       const float* dr = B_s + (it * 8 + g) * KS + hc + t;
-      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], fbits(qr[0]), fbits(qr[4]));
-      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], fbits(qr[8]), fbits(qr[12]));
-      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], fbits(dr[0]), fbits(dr[4]));
-      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], fbits(dr[8]), fbits(dr[12]));
+      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], tfbits(qr[0]), tfbits(qr[4]));
+      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], tfbits(qr[8]), tfbits(qr[12]));
+      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], tfbits(dr[0]), tfbits(dr[4]));
+      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], tfbits(dr[8]), tfbits(dr[12]));
       const int i0 = it * 8 + 2 * t, i1 = i0 + 1;   // query columns of this thread
       const bool v0 = i0 < L, v1 = i1 < L;
       const float l0 = Ls[h * Lp + i0], l1 = Ls[h * Lp + i1];
@@ -243,10 +285,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
       const uint32_t sa1 = tfbits(p2 * (dp[2] - D0)), sa3 = tfbits(p3 * (dp[3] - D1));
       const float* d0 = B_s + (it * 8 + 2 * t) * KS + hc + g;
       const float* q0 = A_s + (it * 8 + 2 * t) * KS + hc + g;
-      mma_tf32(dv[0], pa0, pa1, pa2, pa3, fbits(d0[0]), fbits(d0[KS]));
-      mma_tf32(dv[1], pa0, pa1, pa2, pa3, fbits(d0[8]), fbits(d0[KS + 8]));
-      mma_tf32(dk[0], sa0, sa1, sa2, sa3, fbits(q0[0]), fbits(q0[KS]));
-      mma_tf32(dk[1], sa0, sa1, sa2, sa3, fbits(q0[8]), fbits(q0[KS + 8]));
+      mma_tf32(dv[0], pa0, pa1, pa2, pa3, tfbits(d0[0]), tfbits(d0[KS]));
+      mma_tf32(dv[1], pa0, pa1, pa2, pa3, tfbits(d0[8]), tfbits(d0[KS + 8]));
+      mma_tf32(dk[0], sa0, sa1, sa2, sa3, tfbits(q0[0]), tfbits(q0[KS]));
+      mma_tf32(dk[1], sa0, sa1, sa2, sa3, tfbits(q0[8]), tfbits(q0[KS + 8]));
     }
     if (ja < L) {
       float* dst = dbase + (size_t)ja * 384 + 128 + hc + 2 * t;
@@ -265,31 +307,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   }
 }
 
-template <int NT>
-int launch_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
-               cudaStream_t st) {
-  const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(2 * Lp * KS + Lp) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  attn_fwd_kernel<NT><<<C, 256, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
-  TPC_CHECK_LAUNCH();
-  return TPC_OK;
-}
-
 }  // namespace
 
 int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
                   cudaStream_t st) {
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 208) return TPC_ERR_SHAPE;
-  if (L <= 64) return launch_fwd<8>(qkv, mask, mS, m0, C, L, att, lse, st);
-  if (L <= 104) return launch_fwd<13>(qkv, mask, mS, m0, C, L, att, lse, st);
-  if (L <= 160) return launch_fwd<20>(qkv, mask, mS, m0, C, L, att, lse, st);
-  return launch_fwd<26>(qkv, mask, mS, m0, C, L, att, lse, st);
+  const int Lp = ((L + 7) / 8) * 8;
+  const size_t smem = (size_t)(2 * Lp * KS + Lp) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attn_fwd_kernel<<<C, 512, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
 }
 
 int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
@@ -303,7 +336,7 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
     TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attn_bwd_kernel<<<C, 256, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
+  attn_bwd_kernel<<<C, 512, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

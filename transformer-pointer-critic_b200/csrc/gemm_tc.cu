@@ -27,19 +27,23 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BK = 32;                        // fp32 columns per k-block == one 128-byte swizzle span
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;   // A + B
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // A + B (+ B_lo in 3xTF32 mode)
 constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 320;             // warps 0-3 A_lo splitters, 4-7 epilogue, 8 TMA, 9 MMA
+constexpr int WG_THREADS = 256;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                // 2 x 128 accumulators + STAGES x 32 columns of A_lo
+constexpr int TMEM_ALO = 256;                 // first A_lo column
 
 constexpr int WG_TB = 32;                     // tokens per wgrad stage (4 MMAs of K=8)
 constexpr int WG_STAGES = 6;
 constexpr int WG_BOX_BYTES = WG_TB * BK * 4;  // 4 KB: 32 tokens x 32 features
 constexpr int WG_STAGE_BYTES = 8 * WG_BOX_BYTES;  // X: 4 boxes (128 features) + dY: 4 boxes
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+constexpr int WG_ONES_BYTES = 64 * 128;          // 64 rows x 128 B of 1.0f: A operand of the bias-gradient MMA
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 256 + 1024;
+constexpr int WG_TMEM_COLS = 512;                // 2 x 128 (dW accumulators) + 2 x 128 (column sums)
 
 struct GemmArgs {
   int M, N, K;
@@ -51,6 +55,7 @@ struct GemmArgs {
   float* atomic_out;
   int ld_out;
   int aux_mode, relu, ln, round_out, atomic;
+  int split;   // 3xTF32: D = A.B + A_lo.B + A.B_lo with A_lo = A - trunc(A) built on chip, B_lo from the weight image
   float ln_eps;
 };
 
@@ -64,8 +69,8 @@ __device__ __forceinline__ uint32_t epi_off(int row, int col4 /* col / 4 */) {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmD,
-               const GemmArgs g) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
+               const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
@@ -76,21 +81,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* auxfull = tempty + 2;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 1);
+  uint64_t* lofull = auxfull + 1;        // [STAGES] A_lo of the stage is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lofull + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    if (g.split) tma_prefetch_desc(&tmBlo);
     if (g.aux_mode) tma_prefetch_desc(&tmAux);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&lofull[s], 4);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -99,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(auxfull, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -108,11 +116,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int first = blockIdx.x;
   const int step = gridDim.x;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx = (g.split ? 3 : 2) * TILE_BYTES;
       for (int item = first; item < g.num_items; item += step) {
         const int n_t = item % g.n_tiles;
         const int rest = item / g.n_tiles;
@@ -122,15 +131,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          mbar_expect_tx(&full[stage], tx);
           uint8_t* sa = ring + stage * STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
           tma_load_2d(sa + TILE_BYTES, &tmB, &full[stage], kb * BK, n_t * BN);
+          if (g.split) tma_load_2d(sa + 2 * TILE_BYTES, &tmBlo, &full[stage], kb * BK, n_t * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ A_lo splitters (3xTF32 mode only)
+    // thread == tile row: read its 32 fp32 of the k-block from the swizzled smem tile, keep what the
+    // tensor core's operand truncation drops, park it in TMEM as the A operand of a TS-mode MMA.
+    if (g.split) {
+      const int row = threadIdx.x;  // 0..127 == TMEM lane
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = first; item < g.num_items; item += step) {
+        const int ks = (item / g.n_tiles) % g.k_splits;
+        const int kb0 = ks * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          const uint8_t* sa = ring + stage * STAGE_BYTES + row * 128;
+          float lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
+            lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
+            lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
+          }
+          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
@@ -149,22 +189,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (g.split) mbar_wait(&lofull[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
           const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(sa + TILE_BYTES, 16, 1024);
+          const uint64_t dbl = umma_smem_desc_sw128(sa + 2 * TILE_BYTES, 16, 1024);
+          const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             // advance 8 fp32 (32 B) along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
             umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (g.split) {
+              umma_tf32_ss(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1u);       // trunc(A) . B_lo
+              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);     // A_lo . trunc(B)
+            }
           }
-          umma_commit(&empty[stage]);  // frees the smem stage when these MMAs have read it
+          umma_commit(&empty[stage]);  // frees the smem stage (and its A_lo columns) when these MMAs are done
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);      // accumulator complete
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int et = threadIdx.x - 128;          // 0..127 == accumulator row inside the tile == TMEM lane
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
@@ -299,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -312,19 +359,23 @@ struct WgradArgs {
   int ki_tiles, nj_tiles, splits, tok_per_split, num_items;
   float* dst[4];
   int ld[4];
+  float* bias[4];   // db destination of column tile nj (or nullptr): db += colsum(dY tile), computed by ki == 0 items
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const WgradArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  float* ones = reinterpret_cast<float*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + WG_STAGES;
   uint64_t* tfull = bars + 2 * WG_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the UMMA operand reads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -344,7 +395,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc<WG_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -379,10 +430,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 1, 1);
+      // bias gradient: D2[64][128] += Ones[64][8 tokens] (K-major) * dY tile (MN-major): every row = column sums
+      constexpr uint32_t idesc_ones = umma_idesc_tf32(64, 128, 0, 1);
+      const uint64_t dones = umma_smem_desc_sw128(smem_u32(ones), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int item = first; item < g.num_items; item += step, ++it) {
+        const int nj_i = item % g.nj_tiles;
+        const int ki_i = (item / g.nj_tiles) % g.ki_tiles;
+        const bool do_bias = (ki_i == 0) && (g.bias[nj_i] != nullptr);
         const int sp = (item / g.nj_tiles) / g.ki_tiles;
         const int t0 = sp * g.tok_per_split;
         const int t1 = min(t0 + g.tok_per_split, g.M);
@@ -403,6 +460,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int k = 0; k < WG_TB / 8; ++k) {
             // next 8 tokens: +1024 B -> +64 in the (addr >> 4) field
             umma_tf32_ss(tmem_d, da + 64 * k, db + 64 * k, idesc, (t > t0 || k > 0) ? 1u : 0u);
+            if (do_bias) umma_tf32_ss(tmem_d + 256, dones, db + 64 * k, idesc_ones, (t > t0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -435,6 +493,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (c * 32 + j < ncols) atomicAdd(dst + c * 32 + j, v[j]);
         }
       }
+      if (ki == 0 && g.bias[nj] != nullptr && q == 0) {
+        // rows of the M=64 accumulator are identical; TMEM lane 0 always holds row 0
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + acc * 128 + 256 + c * 32, v);
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < ncols) atomicAdd(g.bias[nj] + c * 32 + j, v[j]);
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -443,7 +514,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 2) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -524,7 +595,7 @@ static int get_tmap(TmapCache* tc, const float* ptr, int rows, int cols, int ld,
 }
 
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
-                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream) {
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const float* Bt_lo) {
   TPC_TRY(gemm_tc_init());
   if (M <= 0) return TPC_OK;
   if (N % BN != 0 || K % BK != 0 || K <= 0) return TPC_ERR_SHAPE;
@@ -543,9 +614,11 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   g.atomic_out = D; g.ld_out = ldd;
   g.aux_mode = epi.aux_mode; g.relu = epi.relu; g.ln = epi.ln; g.round_out = epi.round_out; g.atomic = epi.atomic;
   g.ln_eps = epi.ln_eps;
-  CUtensorMap tA, tB, tAux, tD;
+  g.split = Bt_lo ? 1 : 0;
+  CUtensorMap tA, tB, tBlo, tAux, tD;
   TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
   TPC_TRY(get_tmap(tc, Bt, N, K, ldb, BN, 0, &tB));
+  if (Bt_lo) { TPC_TRY(get_tmap(tc, Bt_lo, N, K, ldb, BN, 0, &tBlo)); } else { tBlo = tB; }
   TPC_TRY(get_tmap(tc, D, M, N, ldd, BM, 0, &tD));
   if (epi.aux_mode) {
     if (!epi.aux) return TPC_ERR_ARG;
@@ -554,7 +627,7 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     tAux = tD;
   }
   const int grid = g.num_items < num_sms ? g.num_items : num_sms;
-  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA, tB, tAux, tD, g);
+  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
@@ -578,12 +651,12 @@ int launch_wgrad(TmapCache* tc, const float* X, int ldx, const float* dY, int ld
   g.tok_per_split = ceil_div(ceil_div(M, splits), WG_TB) * WG_TB;
   g.splits = ceil_div(M, g.tok_per_split);
   g.num_items = out_tiles * g.splits;
-  for (int j = 0; j < 4; ++j) { g.dst[j] = dst.ptr[j]; g.ld[j] = dst.ld[j]; }
+  for (int j = 0; j < 4; ++j) { g.dst[j] = dst.ptr[j]; g.ld[j] = dst.ld[j]; g.bias[j] = dst.bias[j]; }
   CUtensorMap tX, tY;
   TPC_TRY(get_tmap(tc, X, M, Kin, ldx, WG_TB, 1, &tX));
   TPC_TRY(get_tmap(tc, dY, M, Nout, ldy, WG_TB, 1, &tY));
   const int grid = g.num_items < num_sms ? g.num_items : num_sms;
-  wgrad_tc_kernel<<<grid, GEMM_THREADS, WG_SMEM, stream>>>(tX, tY, g);
+  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(tX, tY, g);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

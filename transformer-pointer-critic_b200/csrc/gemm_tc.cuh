@@ -28,14 +28,18 @@ void tmap_cache_destroy(TmapCache*);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes. idempotent.
 
 // D[M,N] = epi(A[M,K] @ Bt[N,K]^T). K % 32 == 0, N % 128 == 0. k_splits > 1 requires epi.atomic.
+// Bt_lo != nullptr selects 3xTF32: Bt holds the raw fp32 weights (the tensor core truncates them), Bt_lo what the
+// truncation drops; the A-side low part is split on chip. Result is fp32-accurate (~2^-21 relative).
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
-                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream);
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream,
+                const float* Bt_lo = nullptr);
 
 // dW[nj][Kin, 128] += X[M,Kin]^T @ dY[M, nj*128 .. nj*128+127]  for every 128-wide column tile nj of dY.
 // dptr[nj] is the destination of tile nj with leading dimension ldd[nj]; accumulation is atomic.
 struct WgradDst {
   float* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
   int ld[4] = {0, 0, 0, 0};
+  float* bias[4] = {nullptr, nullptr, nullptr, nullptr};  // optional: db[128] += colsum(dY tile nj) (fused, same pass)
 };
 int launch_wgrad(TmapCache* tc, const float* X, int ldx, const float* dY, int ldy, int M, int Kin, int Nout,
                  const WgradDst& dst, int num_sms, cudaStream_t stream);

@@ -31,7 +31,7 @@ __global__ void small_dense_fwd_kernel(const float* __restrict__ x, int ldx, con
     // order only; fp32 fma chain keeps |err| ~1e-7
     acc.x = fmaf(xf, w.x, acc.x); acc.y = fmaf(xf, w.y, acc.y); acc.z = fmaf(xf, w.z, acc.z); acc.w = fmaf(xf, w.w, acc.w);
   }
-  reinterpret_cast<float4*>(out + (size_t)r * 128)[c4] = round4(acc);
+  reinterpret_cast<float4*>(out + (size_t)r * 128)[c4] = acc;   // forward activations stay fp32 (3xTF32 consumers)
 }
 
 __global__ void small_dense_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ extra, int rows,
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __rest
   float acc = 0.f;
   for (int j = half; j < S; j += 2) acc = fmaf(ps[h][j], kv[(size_t)j * 384 + 128 + h * 16 + d], acc);
   acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  if (half == 0) ctx[(size_t)c * 128 + h * 16 + d] = tf32_rn(acc);
+  if (half == 0) ctx[(size_t)c * 128 + h * 16 + d] = acc;
 }
 
 __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(const float* __restrict__ dctx, const float* __restrict__ q2,

@@ -38,9 +38,12 @@ struct Builder {
     soff += (n + 255) & ~size_t(255);  // 1 KB alignment keeps every TMA base 16-byte aligned
     return o;
   }
-  // transposed rounded copy of W[in][out] into dst[out][in] (ld = ld_dst) at row offset row0
+  // transposed RAW copy of W[in][out] into dst[out][in] (ld = ld_dst) at row offset row0: forward B operand of the
+  // 3xTF32 GEMM (the tensor core truncates it); the matching low part goes to the mirror half of the image
+  // (patched to dst + shadow_half once the layout is complete: round == 2)
   void job_t(const DenseP& d, size_t dst, int ld_dst, int row0) {
-    jobs->push_back({d.w, dst + (size_t)row0 * ld_dst, d.out, d.in, ld_dst, d.out, 1, 1});
+    jobs->push_back({d.w, dst + (size_t)row0 * ld_dst, d.out, d.in, ld_dst, d.out, 1, 0});
+    jobs->push_back({d.w, dst + (size_t)row0 * ld_dst, d.out, d.in, ld_dst, d.out, 1, 2});
   }
   // rounded copy of W[in][out] into dst[in][ld_dst] at column offset col0
   void job_c(const DenseP& d, size_t dst, int ld_dst, int col0) {
@@ -86,7 +89,8 @@ __global__ void shadow_kernel(const float* __restrict__ params, float* __restric
   for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x) {
     const int r = (int)(i / j.cols), c = (int)(i % j.cols);
     float v = j.transpose ? params[j.src + (size_t)c * j.ld_src + r] : params[j.src + (size_t)r * j.ld_src + c];
-    if (j.round) v = tf32_rn(v);
+    if (j.round == 1) v = tf32_rn(v);
+    else if (j.round == 2) v = tf32_lo(v);
     shadow[j.dst + (size_t)r * j.ld_dst + c] = v;
   }
 }
@@ -197,7 +201,10 @@ int build_layout(const ModelDims& md, bool actor, NetLayout* L, std::vector<Shad
     b.pair(L->h1, &L->h1_t, &L->h1_c);
   }
   L->total = b.off;
-  L->shadow_total = b.soff;
+  L->shadow_half = b.soff;
+  L->shadow_total = 2 * b.soff;   // [main image | low parts of the forward weights at the same offsets]
+  for (ShadowJob& j : *jobs)
+    if (j.round == 2) j.dst += L->shadow_half;
   return TPC_OK;
 }
 

@@ -59,6 +59,7 @@ struct NetLayout {
   int S_critic = 0;
   size_t total = 0;         // canonical parameter count
   size_t shadow_total = 0;  // floats in the shadow buffer
+  size_t shadow_half = 0;   // forward weight W_t at offset o has its 3xTF32 low part at o + shadow_half
   std::vector<TensorInfo> tensors;  // canonical tensors in order (Adam / clipnorm granularity)
 };
 
@@ -69,7 +70,7 @@ struct ShadowJob {
   int ld_dst;                    // leading dimension of destination
   int ld_src;                    // leading dimension of source
   int transpose;                 // 1: dst[r][c] = src[c][r] ; 0: dst[r][c] = src[r][c]
-  int round;                     // RN-round to TF32
+  int round;                     // 0 raw copy | 1 RN-round to TF32 | 2 low part x - trunc_tf32(x)
 };
 
 struct ModelDims {

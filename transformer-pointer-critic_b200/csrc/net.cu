@@ -64,24 +64,29 @@ int gemm(Ctx& cx, const float* A, int lda, const float* Bt, int ldb, float* D, i
   return launch_gemm(cx.tc(), A, lda, Bt, ldb, D, ldd, M, N, K, e, ks, cx.sms(), cx.st);
 }
 
+// forward GEMM: 3xTF32 (fp32-accurate); Bt must be a "_t" entry of the weight image, outputs are not rounded
+int gemm_fwd(Ctx& cx, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+             GemmEpi e, int ks = 1) {
+  if (cx.dry()) return TPC_OK;
+  e.round_out = 0;
+  return launch_gemm(cx.tc(), A, lda, Bt, ldb, D, ldd, M, N, K, e, ks, cx.sms(), cx.st, Bt + cx.L->shadow_half);
+}
+
 // dW (+ db) of a Dense layer whose output gradient is dY[M, Nout]; W canonical [Kin][Nout]
 int dense_grads(Ctx& cx, const float* X, int ldx, const float* dY, int ldy, int M, const DenseP& d) {
   if (cx.dry()) return TPC_OK;
   WgradDst dst;
   const int nj = ceil_div(d.out, 128);
-  for (int j = 0; j < nj; ++j) { dst.ptr[j] = cx.G + d.w + j * 128; dst.ld[j] = d.out; }
-  TPC_TRY(launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, d.in, d.out, dst, cx.sms(), cx.st));
-  return colsum(dY, ldy, M, d.out, cx.G + d.b, cx.st);
+  for (int j = 0; j < nj; ++j) { dst.ptr[j] = cx.G + d.w + j * 128; dst.ld[j] = d.out; dst.bias[j] = cx.G + d.b + j * 128; }
+  return launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, d.in, d.out, dst, cx.sms(), cx.st);
 }
 
 // fused output gradient dY[M, 128 * n] feeding n Dense layers of 128 outputs each (q|k|v or k2|v2|W2)
 int fused_grads(Ctx& cx, const float* X, int ldx, const float* dY, int ldy, int M, const DenseP* const* ds, int n) {
   if (cx.dry()) return TPC_OK;
   WgradDst dst;
-  for (int j = 0; j < n; ++j) { dst.ptr[j] = cx.G + ds[j]->w; dst.ld[j] = 128; }
-  TPC_TRY(launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, 128, 128 * n, dst, cx.sms(), cx.st));
-  for (int j = 0; j < n; ++j) TPC_TRY(colsum(dY + j * 128, ldy, M, 128, cx.G + ds[j]->b, cx.st));
-  return TPC_OK;
+  for (int j = 0; j < n; ++j) { dst.ptr[j] = cx.G + ds[j]->w; dst.ld[j] = 128; dst.bias[j] = cx.G + ds[j]->b; }
+  return launch_wgrad(cx.tc(), X, ldx, dY, ldy, M, 128, 128 * n, dst, cx.sms(), cx.st);
 }
 
 GemmEpi epi_bias(const float* b) { GemmEpi e; e.bias = b; return e; }
@@ -110,14 +115,14 @@ void alloc_layer(Arena& ar, EncLayerActs& a, int rows, int dff) {
 int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int Lt, MaskRef mk, EncLayerActs& a) {
   const int rows = C * Lt, dff = cx.L->dff;
   alloc_layer(*cx.ar, a, rows, dff);
-  TPC_TRY(gemm(cx, x, 128, cx.W + lp.s.wqkv_t, 128, a.qkv, 384, rows, 384, 128, epi_bias(cx.W + lp.s.bqkv)));
+  TPC_TRY(gemm_fwd(cx, x, 128, cx.W + lp.s.wqkv_t, 128, a.qkv, 384, rows, 384, 128, epi_bias(cx.W + lp.s.bqkv)));
   RUN(attention_fwd(a.qkv, mk.mask, mk.mS, mk.m0, C, Lt, a.att, a.lse, cx.st));
-  TPC_TRY(gemm(cx, a.att, 128, cx.W + lp.s.wo_t, 128, a.out1, 128, rows, 128, 128,
+  TPC_TRY(gemm_fwd(cx, a.att, 128, cx.W + lp.s.wo_t, 128, a.out1, 128, rows, 128, 128,
                epi_ln(cx, cx.P + lp.mha.o.b, x, lp.ln1, a.rstd1)));
   GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
   e1.relu = 1;
-  TPC_TRY(gemm(cx, a.out1, 128, cx.W + lp.s.w1_t, 128, a.h, dff, rows, dff, 128, e1));
-  TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w2_t, dff, a.out2, 128, rows, 128, dff,
+  TPC_TRY(gemm_fwd(cx, a.out1, 128, cx.W + lp.s.w1_t, 128, a.h, dff, rows, dff, 128, e1));
+  TPC_TRY(gemm_fwd(cx, a.h, dff, cx.W + lp.s.w2_t, dff, a.out2, 128, rows, 128, dff,
                epi_ln(cx, cx.P + lp.f2.b, a.out1, lp.ln2, a.rstd2)));
   return TPC_OK;
 }
@@ -270,25 +275,25 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
     d.ctx = ar.f((size_t)C * 128); d.o2 = ar.f((size_t)C * 128); d.rstd2 = ar.f(C);
     d.f = ar.f((size_t)C * dff); d.o3 = ar.f((size_t)C * 128); d.rstd3 = ar.f(C);
     // mha1 on a single token: softmax over one key == 1 => attn1 = dense(wv(y)) (actor/decoder_layer.py:22)
-    TPC_TRY(gemm(cx, y, 128, cx.W + lp.s.wv1_t, 128, d.v1, 128, C, 128, 128, epi_bias(cx.P + lp.mha1.v.b)));
-    TPC_TRY(gemm(cx, d.v1, 128, cx.W + lp.s.wo1_t, 128, d.o1, 128, C, 128, 128,
+    TPC_TRY(gemm_fwd(cx, y, 128, cx.W + lp.s.wv1_t, 128, d.v1, 128, C, 128, 128, epi_bias(cx.P + lp.mha1.v.b)));
+    TPC_TRY(gemm_fwd(cx, d.v1, 128, cx.W + lp.s.wo1_t, 128, d.o1, 128, C, 128, 128,
                  epi_ln(cx, cx.P + lp.mha1.o.b, y, lp.ln1, d.rstd1)));
-    TPC_TRY(gemm(cx, d.o1, 128, cx.W + lp.s.wq2_t, 128, d.q2, 128, C, 128, 128, epi_bias(cx.P + lp.mha2.q.b)));
-    TPC_TRY(gemm(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
+    TPC_TRY(gemm_fwd(cx, d.o1, 128, cx.W + lp.s.wq2_t, 128, d.q2, 128, C, 128, 128, epi_bias(cx.P + lp.mha2.q.b)));
+    TPC_TRY(gemm_fwd(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
                  epi_bias(cx.W + lp.s.bkvp)));
     RUN(cross_attn_fwd(d.q2, d.kvw, mha_mask, C, S, d.ctx, d.pc, cx.st));
-    TPC_TRY(gemm(cx, d.ctx, 128, cx.W + lp.s.wo2_t, 128, d.o2, 128, C, 128, 128,
+    TPC_TRY(gemm_fwd(cx, d.ctx, 128, cx.W + lp.s.wo2_t, 128, d.o2, 128, C, 128, 128,
                  epi_ln(cx, cx.P + lp.mha2.o.b, d.o1, lp.ln2, d.rstd2)));
     GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
     e1.relu = 1;
-    TPC_TRY(gemm(cx, d.o2, 128, cx.W + lp.s.w1_t, 128, d.f, dff, C, dff, 128, e1));
-    TPC_TRY(gemm(cx, d.f, dff, cx.W + lp.s.w2_t, dff, d.o3, 128, C, 128, dff,
+    TPC_TRY(gemm_fwd(cx, d.o2, 128, cx.W + lp.s.w1_t, 128, d.f, dff, C, dff, 128, e1));
+    TPC_TRY(gemm_fwd(cx, d.f, dff, cx.W + lp.s.w2_t, dff, d.o3, 128, C, 128, dff,
                  epi_ln(cx, cx.P + lp.f2.b, d.o2, lp.ln3, d.rstd3)));
     y = d.o3;
   }
   a.w1d = ar.f((size_t)C * 128);
   a.score = ar.f((size_t)C * S);
-  TPC_TRY(gemm(cx, y, 128, cx.W + L.w1p_t, 128, a.w1d, 128, C, 128, 128, epi_bias(cx.P + L.W1.b)));
+  TPC_TRY(gemm_fwd(cx, y, 128, cx.W + L.w1p_t, 128, a.w1d, 128, C, 128, 128, epi_bias(cx.P + L.W1.b)));
   RUN(pointer_fwd(a.w1d, a.dec[nl - 1].kvw, cx.P + L.V.w, cx.P + L.V.b, cx.m->dims.clip_C, cx.m->dims.has_clip, ptr_mask,
                   C, S, a.score, logits, probs, argmax, cx.st));
   return TPC_OK;
@@ -386,9 +391,8 @@ int critic_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, in
   int ks = ceil_div(cx.sms(), ceil_div(C, 128));
   if (ks > K / 32 / 4) ks = K / 32 / 4;
   if (ks < 1) ks = 1;
-  TPC_TRY(gemm(cx, a.enc.enc_out, K, cx.W + L.h0_t, K, a.h0, 128, C, 128, K, e, ks));   // Flatten -> Dense(128)
-  RUN(round_tf32_inplace(a.h0, (size_t)C * 128, cx.st));
-  TPC_TRY(gemm(cx, a.h0, 128, cx.W + L.h1_t, 128, a.h1, 128, C, 128, 128, epi_bias(cx.P + L.h1.b)));
+  TPC_TRY(gemm_fwd(cx, a.enc.enc_out, K, cx.W + L.h0_t, K, a.h0, 128, C, 128, K, e, ks));   // Flatten -> Dense(128)
+  TPC_TRY(gemm_fwd(cx, a.h0, 128, cx.W + L.h1_t, 128, a.h1, 128, C, 128, 128, epi_bias(cx.P + L.h1.b)));
   RUN(value_head_fwd(a.h1, cx.P + L.hv.w, cx.P + L.hv.b, C, values, cx.st));
   return TPC_OK;
 }

@@ -35,10 +35,11 @@ int tpc_destroy(tpc_handle* h) {
 int tpc_num_sms(const tpc_handle* h) { return h ? h->num_sms : 0; }
 
 // D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags: bit0 relu, bit1 layernorm(+rstd), bit2 round_out,
-// bit3 atomic split-K; aux_mode 0/1/2 (none / add / relu-gate).
+// bit3 atomic split-K; aux_mode 0/1/2 (none / add / relu-gate). Bt_lo != NULL: 3xTF32 (Bt raw fp32, Bt_lo = Bt -
+// trunc_tf32(Bt)), fp32-accurate result.
 int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
              const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
-             float* rstd_out, int flags, int k_splits, void* stream) {
+             float* rstd_out, int flags, int k_splits, const float* Bt_lo, void* stream) {
   if (!h) return TPC_ERR_ARG;
   GemmEpi e;
   e.bias = bias;
@@ -52,12 +53,13 @@ int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, f
   e.ln = (flags & 2) ? 1 : 0;
   e.round_out = (flags & 4) ? 1 : 0;
   e.atomic = (flags & 8) ? 1 : 0;
-  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream);
+  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream, Bt_lo);
 }
 
-// dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout]   (dW row-major with leading dimension ldw, atomically accumulated)
-int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int M, int Kin,
-              int Nout, void* stream) {
+// dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout]   (dW row-major with leading dimension ldw, atomically accumulated);
+// db[Nout] += colsum(dY) when db != NULL (fused into the same pass)
+int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int M,
+              int Kin, int Nout, void* stream) {
   if (!h) return TPC_ERR_ARG;
   WgradDst d;
   const int nj = ceil_div(Nout, 128);
@@ -65,6 +67,7 @@ int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, 
   for (int j = 0; j < nj; ++j) {
     d.ptr[j] = dW + j * 128;
     d.ld[j] = ldw;
+    d.bias[j] = db ? db + j * 128 : nullptr;
   }
   return launch_wgrad(h->tmaps, X, ldx, dY, ldy, M, Kin, Nout, d, h->num_sms, (cudaStream_t)stream);
 }

@@ -57,8 +57,9 @@ SIGNATURES = {
     "tpc_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     "tpc_a2c_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     "tpc_gemm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "tpc_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+                         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tpc_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                          c_void_p]),
     "tpc_actor_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tpc_critic_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
