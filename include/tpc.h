@@ -73,6 +73,8 @@ typedef struct tpc_env_config {
 int tpc_create(tpc_handle** out);
 int tpc_destroy(tpc_handle* h);
 int tpc_num_sms(const tpc_handle* h);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long tpc_launch_count(void);
 
 /* replaces model_factory('transformer', opts) (agents/models/model_factory.py:4-36) */
 int tpc_model_create(tpc_handle* h, const tpc_model_config* cfg, tpc_model** out);

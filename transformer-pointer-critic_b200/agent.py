@@ -1,0 +1,291 @@
+"""Agent with the reference's interface (agents/agent.py:15-305) on top of the libtpc engine.
+
+Two ways to drive it:
+  * step-wise, exactly like the reference (`act` / `store` / `compute_*`): every model evaluation is a libtpc
+    forward call; arrays cross the API as host NumPy like in the reference (compatibility mode, used by tests);
+  * fused (`rollout` + `update`): the whole T-step rollout and the A2C update run on the device behind two
+    C-ABI calls (tpc_rollout, tpc_a2c_grads + tpc_adam_apply); this is what `trainer` / `tester` use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .engine import Engine, RolloutTensors, model_config_from_agent_config
+from .env import HostTensor
+
+TRANSFORMER = "transformer"
+
+
+def _dev(x, device, dtype=torch.float32):
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+
+
+def reshape_into_vertical_format(data, batch_size):
+    """environment/custom/resource_v3/misc/utils.py:13-17: (B,T) -> (T*B,1), step-major."""
+    return np.reshape(np.transpose(np.asarray(data), [1, 0]), [batch_size, 1])
+
+
+def reshape_into_horizontal_format(data, batch_size, decoding_steps):
+    """environment/custom/resource_v3/misc/utils.py:7-11."""
+    return np.transpose(np.reshape(np.asarray(data), [decoding_steps, batch_size]), [1, 0])
+
+
+class _Net:
+    """Stands in for the Keras model objects `agent.bin_actor` / `agent.critic`."""
+
+    def __init__(self, agent: "Agent", which: int):
+        self.agent, self.which = agent, which
+
+    @property
+    def engine(self) -> Engine:
+        return self.agent.engine
+
+    @property
+    def trainable_weights(self):
+        offs, sizes = self.engine.layout(self.which)
+        flat = self.engine.params[self.which]
+        return [flat[o:o + n] for o, n in zip(offs, sizes)]
+
+    def get_flat(self) -> np.ndarray:
+        return self.engine.params[self.which].detach().cpu().numpy().copy()
+
+    def set_flat(self, flat) -> None:
+        self.engine.set_params(self.which, flat)
+
+    def save_weights(self, location: str) -> None:
+        os.makedirs(os.path.dirname(os.path.abspath(location)) or ".", exist_ok=True)
+        offs, sizes = self.engine.layout(self.which)
+        np.savez(location if location.endswith(".npz") else location + ".npz", flat=self.get_flat(),
+                 offsets=np.asarray(offs), sizes=np.asarray(sizes))
+
+    def load_weights(self, location: str) -> None:
+        path = location if location.endswith(".npz") else location + ".npz"
+        self.set_flat(np.load(path)["flat"])
+
+    def __call__(self, *args, **kwargs):
+        if self.which == 0:
+            # ActorTransformer.call(enc_input, dec_input, attention_mask, training, num_bins, enc_padding_mask=...)
+            state, dec_input, attention_mask, _training, num_bins = args[:5]
+            mha = kwargs.get("enc_padding_mask")
+            dev = self.engine.device
+            st = _dev(state, dev)
+            B, S = st.shape[0], st.shape[1]
+            logits, probs, idx = self.engine.actor_forward(st, _dev(dec_input, dev).reshape(B, -1),
+                                                           _dev(attention_mask, dev), _dev(mha, dev).reshape(B, S),
+                                                           num_bins)
+            i = idx.cpu().numpy()
+            decoded = np.asarray(state)[np.arange(B), i] if not torch.is_tensor(state) else state[torch.arange(B), idx.long()]
+            return (logits.cpu().numpy().view(HostTensor), probs.cpu().numpy().view(HostTensor), i.view(HostTensor),
+                    decoded)
+        # CriticTransformer.call(encoder_input, training, num_bins, enc_padding_mask)
+        state, _training, num_bins = args[:3]
+        mha = kwargs.get("enc_padding_mask", args[3] if len(args) > 3 else None)
+        dev = self.engine.device
+        st = _dev(state, dev)
+        v = self.engine.critic_forward(st, _dev(mha, dev).reshape(st.shape[0], st.shape[1]), num_bins)
+        return v.cpu().numpy().reshape(-1, 1).view(HostTensor)
+
+
+class _Adam:
+    """tf.keras.optimizers.Adam(learning_rate, clipnorm) (agents/agent.py:39-49) -> tpc_adam_apply."""
+
+    def __init__(self, agent: "Agent", which: int, learning_rate: float, clipnorm):
+        self.agent, self.which = agent, which
+        self.learning_rate, self.clipnorm = learning_rate, clipnorm
+
+    def apply_gradients(self, grads_and_vars=None, grad_scale: float = 1.0):
+        """Applies the gradients currently held in the engine's gradient buffer of this network."""
+        self.agent.engine.adam_apply(self.which, self.learning_rate, self.clipnorm, grad_scale)
+
+
+class Agent:
+    def __init__(self, name, opts, device="cuda:0", num_features=None, seed: int = 0):
+        self.name = name
+        self.agent_config = opts
+        self.training = True
+        self.batch_size: int = opts["batch_size"]
+        self.num_resources: int = opts["num_resources"]
+        self.num_bins: int = opts["num_bins"]
+        self.tensor_size: int = opts["tensor_size"]
+        self.gamma: float = opts["gamma"]
+        self.values_loss_coefficient: float = opts["values_loss_coefficient"]
+        self.entropy_coefficient: float = opts["entropy_coefficient"]
+        self.stochastic_action_selection: bool = opts["stochastic_action_selection"]
+        self.critic_learning_rate = opts["critic"]["learning_rate"]
+        self.critic_clipnorm = opts["critic"]["clipnorm"]
+        self.actor_learning_rate = opts["actor"]["learning_rate"]
+        self.actor_clipnorm = opts["actor"]["clipnorm"]
+        if name != TRANSFORMER:
+            raise ValueError(f"unknown agent type {name!r} (model_factory.py:35 returns None for it)")
+        emb = opts["encoder_embedding"]
+        if num_features is None:
+            num_features = emb.get("num_resource_features") or 3
+        self.num_features = num_features
+        self.engine = Engine(model_config_from_agent_config(opts, num_features), device)
+        self.bin_actor, self.critic = _Net(self, 0), _Net(self, 1)
+        self.critic_opt = _Adam(self, 1, self.critic_learning_rate, self.critic_clipnorm)
+        self.pointer_opt = _Adam(self, 0, self.actor_learning_rate, self.actor_clipnorm)
+        self.init_weights(seed)
+        self.sample_seed = 0x5EED + seed
+        self.episode_id0 = 0
+        self._draw = 0
+        self.clear_memory()
+
+    # ------------------------------------------------------------------ weights
+    def init_weights(self, seed: int = 0) -> None:
+        """Keras defaults: glorot_uniform kernels (or U(+-1/sqrt(dims)), common/utils.py:49-64), zero biases,
+        LayerNorm gamma 1 / beta 0."""
+        rng = np.random.default_rng(seed)
+        for which, sub in ((0, "actor"), (1, "critic")):
+            offs, sizes = self.engine.layout(which)
+            flat = np.zeros(self.engine.n_params[which], dtype=np.float32)
+            default = self.agent_config[sub].get("use_default_initializer", True)
+            # the canonical list alternates (kernel, bias) for Dense and (gamma, beta) for LayerNorm; a LayerNorm
+            # pair is the only one with equal sizes (no Dense here has a single input feature)
+            for i in range(0, len(offs), 2):
+                n, nb = sizes[i], sizes[i + 1]
+                if n == nb:
+                    flat[offs[i]:offs[i] + n] = 1.0
+                else:
+                    fan_out, fan_in = nb, n // nb
+                    lim = np.sqrt(6.0 / (fan_in + fan_out)) if default else 1.0 / np.sqrt(
+                        self.agent_config[sub]["dim_model"])
+                    flat[offs[i]:offs[i] + n] = rng.uniform(-lim, lim, size=n).astype(np.float32)
+            self.engine.set_params(which, flat)
+
+    def save_weights(self, location):
+        self.bin_actor.save_weights(location)
+
+    def load_weights(self, location):
+        self.bin_actor.load_weights(location)
+
+    def set_testing_mode(self, batch_size, num_bins, num_resources):
+        """agents/agent.py:296-305."""
+        self.training = False
+        self.stochastic_action_selection = False
+        self.batch_size = batch_size
+        self.num_resources = num_resources
+        self.num_bins = num_bins
+
+    # ------------------------------------------------------------------ memory (agents/agent.py:75-108)
+    def store(self, state, dec_input, bin_mask, mha_mask, bin, reward, training_step):
+        self.states.append(state)
+        self.actor_decoder_input.append(dec_input)
+        self.bin_masks.append(bin_mask)
+        self.mha_masks.append(mha_mask)
+        self.bins.append(bin)
+        self.rewards[:, training_step] = np.asarray(reward)[:, 0]
+
+    def clear_memory(self):
+        self.states = []
+        self.actor_decoder_input = []
+        self.bin_masks = []
+        self.mha_masks = []
+        self.bins = []
+        self.rewards = np.zeros((self.batch_size, self.num_resources), dtype="float32")
+
+    # ------------------------------------------------------------------ step-wise API
+    def act(self, state, dec_input, bins_mask, mha_used_mask, build_feasible_mask):
+        """agents/agent.py:244-287."""
+        bins_mask = build_feasible_mask(state, dec_input, bins_mask)
+        _logits, bins_probs, bin_ids, _ = self.bin_actor(state, dec_input, bins_mask, self.training, self.num_bins,
+                                                         enc_padding_mask=mha_used_mask,
+                                                         dec_padding_mask=mha_used_mask)
+        if self.stochastic_action_selection:
+            dev = self.engine.device
+            p = _dev(np.asarray(bins_probs), dev)
+            out = torch.empty(p.shape[0], dtype=torch.int32, device=dev)
+            L.check(self.engine.lib.tpc_sample_categorical(self.engine.h, L.ptr(p), p.shape[0], p.shape[1],
+                                                           self.sample_seed, self.episode_id0, self._draw, L.ptr(out),
+                                                           self.engine.stream), "tpc_sample_categorical")
+            self._draw += 1
+            bin_ids = out.cpu().numpy().view(HostTensor)
+        return bin_ids, bins_mask, bins_probs
+
+    def compute_discounted_rewards(self, bootstrap_state_value):
+        """agents/agent.py:110-124 (host arithmetic on the (B,T) reward table, as in the reference)."""
+        boot = np.asarray(bootstrap_state_value, dtype=np.float32).reshape(-1)
+        out = np.zeros_like(self.rewards)
+        for step in reversed(range(self.rewards.shape[1])):
+            est = self.rewards[:, step] + np.float32(self.gamma) * boot
+            out[:, step] = est
+            boot = est
+        return out
+
+    def compute_value_loss(self, discounted_rewards):
+        """agents/agent.py:126-166 -> (value_loss, state_values, advantages)."""
+        states = np.concatenate(self.states, axis=0)
+        n = states.shape[0]
+        mha = np.concatenate(self.mha_masks, axis=0)
+        values = np.asarray(self.critic(states, self.training, self.num_bins, enc_padding_mask=mha))
+        R = reshape_into_vertical_format(discounted_rewards, n).astype(np.float32)
+        adv = R - values
+        loss = np.float32(self.values_loss_coefficient) * np.mean((R - values) ** 2, axis=-1)
+        return np.mean(loss, axis=-1), values.view(HostTensor), adv.view(HostTensor)
+
+    def compute_actor_loss(self, model, masks, actions, decoder_inputs, advantages):
+        """agents/agent.py:168-242 -> (total_loss, dec_output, entropy, policy_loss, probs)."""
+        states = np.concatenate(self.states, axis=0)
+        attention_mask = np.concatenate(masks, axis=0)
+        mha = np.concatenate(self.mha_masks, axis=0)
+        dec_input = np.concatenate(decoder_inputs, axis=0)
+        logits, probs, _idx, dec_out = model(states, dec_input, attention_mask, self.training, self.num_bins,
+                                             enc_padding_mask=mha, dec_padding_mask=mha)
+        logits = np.asarray(logits, dtype=np.float32)
+        probs = np.asarray(probs, dtype=np.float32)
+        acts = np.concatenate([np.asarray(a) for a in actions], axis=0).astype(np.int64)
+        mx = logits.max(axis=-1, keepdims=True)
+        logp = logits - (mx + np.log(np.exp(logits - mx).sum(axis=-1, keepdims=True)))
+        policy_loss = -logp[np.arange(len(acts)), acts]
+        entropy = -(probs * logp).sum(axis=-1)
+        total = np.mean(policy_loss * np.asarray(advantages).reshape(-1) - self.entropy_coefficient * entropy, axis=-1)
+        return total, dec_out, entropy.view(HostTensor), policy_loss.view(HostTensor), probs.view(HostTensor)
+
+    # ------------------------------------------------------------------ fused device path
+    def memory_to_device(self) -> RolloutTensors:
+        """Upload the step-wise memory (lists filled by `store`) into device trajectory buffers."""
+        T, B = len(self.states), self.states[0].shape[0]
+        N, R, F = self.num_bins, self.num_resources, self.num_features
+        S = N + R
+        states = np.stack(self.states)
+        cost = states.shape[-1] > F
+        bufs = RolloutTensors(B, N, R, F, self.engine.device, cost=cost)
+        bufs.states.copy_(_dev(states[..., :F], self.engine.device))
+        if cost:
+            bufs.is_empties.copy_(_dev(states[..., F], self.engine.device))
+        bufs.dec_inputs.copy_(_dev(np.stack(self.actor_decoder_input).reshape(T, B, F), self.engine.device))
+        bufs.ptr_masks.copy_(_dev(np.stack(self.bin_masks), self.engine.device))
+        bufs.mha_masks.copy_(_dev(np.stack(self.mha_masks).reshape(T, B, S), self.engine.device))
+        bufs.actions.copy_(_dev(np.stack([np.asarray(b) for b in self.bins]), self.engine.device, torch.int32))
+        bufs.rewards.copy_(_dev(self.rewards, self.engine.device))
+        return bufs
+
+    def update(self, bufs: RolloutTensors, world_size: int = 1, allreduce=None, chunk_states: int = 0):
+        """trainer.py:103-156 on device: returns, value loss, actor loss, both backward passes, both Adam steps.
+        `allreduce(tensor)` sums a device tensor over the data-parallel ranks (None for one process).
+        Returns the 4 reported scalars (value_loss, mean policy loss, total actor loss, mean entropy)."""
+        n_local = bufs.B * bufs.R
+        total = n_local * world_size
+        self.engine.a2c_grads(bufs, self.gamma, self.values_loss_coefficient, self.entropy_coefficient,
+                              chunk_states=chunk_states, total_states=total)
+        losses = self.engine.losses
+        if allreduce is not None and world_size > 1:
+            allreduce(self.engine.grads[1])
+            allreduce(self.engine.grads[0])
+            allreduce(losses)
+        self.critic_opt.apply_gradients()
+        self.pointer_opt.apply_gradients()
+        return losses / float(total)
+
+    def rollout(self, env, bufs: RolloutTensors, greedy=None):
+        """T steps of act -> env.step on device (trainer.py:49-100 / tester.py:173-209)."""
+        greedy = (not self.stochastic_action_selection) if greedy is None else greedy
+        self.engine.rollout(env._cfg_struct(), bufs, greedy, self.sample_seed, env.episode_id0, self._draw)
+        self._draw += 1

@@ -18,7 +18,14 @@
     }                                                                                 \
   } while (0)
 
-#define TPC_CHECK_LAUNCH() TPC_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by TPC_CHECK_LAUNCH(): it also feeds the launch counter that
+// bench.py reports as `gpu_launches` (tpc_launch_count()).
+extern unsigned long long g_tpc_launches;
+#define TPC_CHECK_LAUNCH()                 \
+  do {                                     \
+    ++g_tpc_launches;                      \
+    TPC_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 #define TPC_TRY(expr)            \
   do {                           \

@@ -4,7 +4,11 @@
 
 using namespace tpc;
 
+unsigned long long g_tpc_launches = 0;
+
 extern "C" {
+
+unsigned long long tpc_launch_count(void) { return g_tpc_launches; }
 
 int tpc_create(tpc_handle** out) {
   if (!out) return TPC_ERR_ARG;

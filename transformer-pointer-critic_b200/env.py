@@ -1,0 +1,272 @@
+"""Device-resident ResourceV3 / KnapsackV2 environments with the reference's Python interface
+(environment/custom/resource_v3/env.py:21-447, environment/custom/knapsack_v2/env.py).
+
+State lives in HBM (torch-allocated); every transition is a libtpc kernel (csrc/env.cu). The step-wise methods
+(`reset/state/step/build_feasible_mask`) return host NumPy arrays exactly like the reference so that code
+written against it keeps working; the fused trainer / tester use `device_buffers()` and never leave the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .engine import REWARD_TYPES, RolloutTensors, env_config_struct
+
+
+class HostTensor(np.ndarray):
+    """ndarray with the `.numpy()` accessor the reference's trainer calls on TF tensors (trainer.py:73-74)."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def _host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+class _DeviceEnvBase:
+    KIND = 0
+
+    def __init__(self, name: str, opts: dict, device="cuda:0", seed_stream: int = 0):
+        self.name = name
+        self.opts = opts
+        self.device = torch.device(device)
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        L.check(self.lib.tpc_create(C.byref(self.h)), "tpc_create")
+        self.gather_stats = False
+        self.mask_nodes_in_mha = opts["mask_nodes_in_mha"]
+        self.normalization_factor = opts["normalization_factor"]
+        self.decimal_precision = opts["decimal_precision"]
+        self.batch_size = opts["batch_size"]
+        self.num_features = opts["num_features"]
+        self.EOS_CODE = opts["EOS_CODE"]
+        self.EOS_BIN = np.full((1, self.num_features), self.EOS_CODE, dtype="float32")
+        self.seed_value = int(opts.get("seed_value", 1235))
+        self.episode_id0 = 0          # first global episode id of this process (data-parallel ranks differ)
+        self.epoch = 0                # reset counter: a new Philox stream per reset
+        self.history = []
+        self._cfg = None
+        self.profiles = None
+
+    # -- properties the subclasses define: node_sample_size (incl. EOS), profiles_sample_size --------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def tensor_size(self):
+        return self.node_sample_size + self.profiles_sample_size
+
+    @property
+    def is_cost(self):
+        return False
+
+    def _cfg_struct(self):
+        return self._cfg
+
+    def _alloc(self):
+        B, S, F = self.batch_size, self.tensor_size, self.num_features
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.batch_d, self.bin_net_mask_d, self.mha_mask_d = f(B, S, F), f(B, S), f(B, S)
+        self.resource_net_mask_d = f(B, S)
+        self.is_empty_d = f(B, S) if self.is_cost else None
+
+    def generate_dataset(self):
+        """env.py:205-215 on device (Philox stream keyed by seed_value)."""
+        e = self._cfg_struct()
+        if e.num_profiles <= 0:
+            return None
+        prof = torch.empty(e.num_profiles, self.num_features, dtype=torch.float32, device=self.device)
+        L.check(self.lib.tpc_env_generate_profiles(self.h, C.byref(e), self.seed_value, L.ptr(prof), self.stream))
+        return prof
+
+    def reset(self):
+        """env.py:83-99."""
+        self.decoding_step = self.node_sample_size
+        self._alloc()
+        e = self._cfg_struct()
+        L.check(self.lib.tpc_env_reset(self.h, C.byref(e), self.seed_value, self.episode_id0, self.epoch,
+                                       L.ptr(self.profiles), self.batch_size, self.node_sample_size,
+                                       self.profiles_sample_size, L.ptr(self.batch_d), L.ptr(self.bin_net_mask_d),
+                                       L.ptr(self.mha_mask_d), L.ptr(self.is_empty_d), self.stream), "tpc_env_reset")
+        self.resource_net_mask_d.copy_(1.0 - self.bin_net_mask_d)
+        self.epoch += 1
+        if self.gather_stats:
+            self.history = None  # per-instance Python history objects are replaced by device statistics (tester.py)
+        return self.state()
+
+    def load_batch(self, batch) -> None:
+        """Install a given (B,S,F) instance tensor (tests / reproducing a stored problem)."""
+        batch = torch.as_tensor(np.asarray(batch, dtype=np.float32)[:, :, : self.num_features])
+        self.batch_size = batch.shape[0]
+        self.decoding_step = self.node_sample_size
+        self._alloc()
+        self.batch_d.copy_(batch.to(self.device))
+        self.bin_net_mask_d[:, self.node_sample_size:] = 1
+        self.resource_net_mask_d[:, : self.node_sample_size] = 1
+        if self.is_cost:
+            self.is_empty_d[:, 0] = self.EOS_CODE
+
+    def _state_host(self):
+        batch = _host(self.batch_d)
+        if self.is_cost:  # add_is_empty_dim (env.py:424-426)
+            batch = np.concatenate([batch, _host(self.is_empty_d)[:, :, None]], axis=-1)
+        return batch
+
+    def state(self):
+        """env.py:101-113 -> (state, decoder_input, bin_net_mask, mha_used_mask) as host arrays."""
+        batch = self._state_host()
+        dec = np.expand_dims(batch[:, self.decoding_step, : self.num_features], axis=1)
+        return batch, dec, _host(self.bin_net_mask_d), _host(self.mha_mask_d)[:, None, None, :]
+
+    def build_feasible_mask(self, state, resources, bin_net_mask):
+        """env.py:387-422 on device; accepts host or device arrays, returns a host array."""
+        st = torch.as_tensor(np.ascontiguousarray(state, dtype=np.float32)).to(self.device)
+        dec = torch.as_tensor(np.ascontiguousarray(resources, dtype=np.float32)).to(self.device).reshape(st.shape[0], -1)
+        bm = torch.as_tensor(np.ascontiguousarray(bin_net_mask, dtype=np.float32)).to(self.device)
+        out = torch.empty_like(bm)
+        e = self._cfg_struct()
+        L.check(self.lib.tpc_env_feasible_mask(self.h, C.byref(e), L.ptr(st), st.shape[2], L.ptr(dec), L.ptr(bm),
+                                               st.shape[0], st.shape[1], L.ptr(out), self.stream))
+        return _host(out)
+
+    def step(self, bin_ids, feasible_bin_mask):
+        """env.py:115-203."""
+        ids = torch.as_tensor(np.asarray(bin_ids, dtype=np.int32)).to(self.device)
+        B = self.batch_size
+        reward = torch.empty(B, dtype=torch.float32, device=self.device)
+        e = self._cfg_struct()
+        L.check(self.lib.tpc_env_step(self.h, C.byref(e), L.ptr(self.batch_d), L.ptr(self.bin_net_mask_d),
+                                      L.ptr(self.resource_net_mask_d), L.ptr(self.mha_mask_d), L.ptr(self.is_empty_d),
+                                      L.ptr(ids), self.decoding_step, B, self.node_sample_size,
+                                      self.profiles_sample_size, L.ptr(reward), self.stream), "tpc_env_step")
+        res_mask = _host(self.resource_net_mask_d)
+        is_done = bool(np.all(res_mask == 1))
+        info = {"bin_net_mask": _host(self.bin_net_mask_d), "resource_net_mask": res_mask,
+                "mha_used_mask": _host(self.mha_mask_d)[:, None, None, :]}
+        self.decoding_step += 1
+        batch = self._state_host()
+        if self.decoding_step < self.tensor_size:
+            dec = np.expand_dims(batch[:, self.decoding_step, : self.num_features], axis=1)
+        else:
+            dec = np.array([None])
+        rewards = _host(reward).reshape(B, 1).view(HostTensor)
+        return batch, dec, rewards, is_done, info
+
+    # -- fused path ----------------------------------------------------------------------------------------
+    def device_buffers(self, store=True, keep_logits=False) -> RolloutTensors:
+        """Fresh trajectory buffers whose live-state tensors alias this env's device state."""
+        bufs = RolloutTensors(self.batch_size, self.node_sample_size, self.profiles_sample_size, self.num_features,
+                              self.device, cost=self.is_cost, store=store, keep_logits=keep_logits)
+        return bufs
+
+    def reset_into(self, bufs: RolloutTensors) -> None:
+        """reset() writing straight into rollout buffers (no host copies)."""
+        e = self._cfg_struct()
+        L.check(self.lib.tpc_env_reset(self.h, C.byref(e), self.seed_value, self.episode_id0, self.epoch,
+                                       L.ptr(self.profiles), bufs.B, bufs.N, bufs.R, L.ptr(bufs.batch),
+                                       L.ptr(bufs.bin_net_mask), L.ptr(bufs.mha_mask), L.ptr(bufs.is_empty),
+                                       self.stream), "tpc_env_reset")
+        self.epoch += 1
+
+    def store_dataset(self, location) -> None:
+        """env.py:443-444."""
+        np.savetxt(location, _host(self.profiles) if self.profiles is not None else np.zeros((0, self.num_features)))
+
+    def load_dataset(self, location):
+        """env.py:446-447."""
+        self.profiles = torch.as_tensor(np.loadtxt(location).astype(np.float32)).to(self.device).contiguous()
+        self._cfg.num_profiles = self.profiles.shape[0]
+
+
+class ResourceEnvironmentV3(_DeviceEnvBase):
+    """environment/custom/resource_v3/env.py:20-447."""
+    KIND = 0
+
+    def __init__(self, name: str, opts: dict, device="cuda:0"):
+        super().__init__(name, opts, device)
+        self.generate_request_on_the_fly = opts["generate_request_on_the_fly"]
+        self.num_profiles = opts["num_profiles"]
+        self.profiles_sample_size = opts["profiles_sample_size"]
+        assert self.num_profiles >= self.profiles_sample_size, \
+            "Resource sample size should be less than total number of resources"
+        self.node_sample_size = opts["node_sample_size"] + 1  # + EOS node (env.py:48)
+        self.req_min_val, self.req_max_val = opts["req_min_val"], opts["req_max_val"]
+        self.node_min_val, self.node_max_val = opts["node_min_val"], opts["node_max_val"]
+        if opts["reward"]["type"] not in REWARD_TYPES:
+            raise NameError(f"Unknown Reward Name! Select one of {list(REWARD_TYPES.keys())}")
+        self.reward_type = opts["reward"]["type"]
+        self._cfg = env_config_struct(opts, 0)
+        self.decoding_step = self.node_sample_size
+        self.profiles = self.total_profiles = self.generate_dataset()
+        self.reset()
+
+    @property
+    def is_cost(self):
+        return self.reward_type == "reduced_node_usage"
+
+    def add_stats_to_agent_config(self, agent_config: dict):
+        """env.py:314-334."""
+        agent_config["num_resources"] = self.profiles_sample_size
+        agent_config["num_bins"] = self.node_sample_size
+        agent_config["tensor_size"] = self.node_sample_size + self.profiles_sample_size
+        agent_config["batch_size"] = self.batch_size
+        agent_config["encoder_embedding"] = {}
+        if self.is_cost:
+            agent_config["encoder_embedding"].update(common=False, num_bin_features=4, num_resource_features=3)
+        else:
+            agent_config["encoder_embedding"].update(common=True, num_bin_features=None, num_resource_features=None)
+        return agent_config
+
+    def set_testing_mode(self, batch_size, node_sample_size, profiles_sample_size, node_min_val, node_max_val) -> None:
+        """env.py:336-352."""
+        self.gather_stats = True
+        self.batch_size = batch_size
+        self.node_min_val, self.node_max_val = node_min_val, node_max_val
+        self._cfg.node_min_val, self._cfg.node_max_val = node_min_val, node_max_val
+        self.node_sample_size = node_sample_size + 1
+        self.profiles_sample_size = profiles_sample_size
+
+
+class KnapsackEnvironmentV2(_DeviceEnvBase):
+    """environment/custom/knapsack_v2/env.py (same agent-facing interface, 2 features)."""
+    KIND = 1
+
+    def __init__(self, name: str, opts: dict, device="cuda:0"):
+        super().__init__(name, opts, device)
+        self.item_sample_size = self.profiles_sample_size = opts["item_sample_size"]
+        self.bin_sample_size = self.node_sample_size = opts["bin_sample_size"] + 1
+        self.reward_type = "greedy"
+        self._cfg = env_config_struct(opts, 1)
+        self.decoding_step = self.node_sample_size
+        self.profiles = self.total_items = self.generate_dataset()
+        self.reset()
+
+    def add_stats_to_agent_config(self, agent_config: dict):
+        """knapsack_v2/env.py:318-332: always separate embeddings with 2 / 2 features."""
+        agent_config["num_resources"] = self.item_sample_size
+        agent_config["num_bins"] = self.bin_sample_size
+        agent_config["tensor_size"] = self.bin_sample_size + self.item_sample_size
+        agent_config["batch_size"] = self.batch_size
+        agent_config["encoder_embedding"] = {"common": False, "num_bin_features": 2, "num_resource_features": 2}
+        return agent_config
+
+    def set_testing_mode(self, batch_size, bin_sample_size, item_sample_size, *_):
+        self.gather_stats = True
+        self.batch_size = batch_size
+        self.bin_sample_size = self.node_sample_size = bin_sample_size + 1
+        self.item_sample_size = self.profiles_sample_size = item_sample_size
+
+
+def env_factory(type: str, name: str, opts: dict, device="cuda:0"):
+    """environment/env_factory.py:27-33 -> (env, tester)."""
+    from .tester import test as resource_tester
+    table = {"ResourceV3": (ResourceEnvironmentV3, resource_tester), "KnapsackV2": (KnapsackEnvironmentV2, resource_tester)}
+    if type != "custom" or name not in table:
+        raise NameError(f"Unknown environment {type}/{name}")
+    env_cls, tester = table[name]
+    return env_cls(name, opts, device), tester

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tpc_create": (c_int, [C.POINTER(c_void_p)]),
     "tpc_destroy": (c_int, [c_void_p]),
     "tpc_num_sms": (c_int, [c_void_p]),
+    "tpc_launch_count": (C.c_ulonglong, []),
     "tpc_model_create": (c_int, [c_void_p, C.POINTER(ModelConfig), C.POINTER(c_void_p)]),
     "tpc_model_destroy": (c_int, [c_void_p]),
     "tpc_param_count": (c_size_t, [c_void_p, c_int]),
