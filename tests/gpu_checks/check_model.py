@@ -160,6 +160,7 @@ def main():
             worst[f"grad_{N}_{R}_{chunk}"] = max(ptc[wc], pta[wa])
         eng.close()
     print("WORST", {k: f"{v:.2e}" for k, v in worst.items()})
+    return worst
 
 
 if __name__ == "__main__":

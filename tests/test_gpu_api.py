@@ -1,0 +1,127 @@
+"""GPU tests of the reference-facing Python API (Agent / env / trainer / tester) and full-size property tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(batch=8, nodes=5, rules=7, reward="greedy"):
+    import torch
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import ResourceEnvironmentV3
+    agent_cfg, trainer_cfg, env_cfg, tester_cfg, _, _ = get_configs("ResourceV3", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=batch, node_sample_size=nodes, profiles_sample_size=rules)
+    env_cfg["reward"]["type"] = reward
+    env = ResourceEnvironmentV3("ResourceV3", env_cfg, "cuda:0")
+    env.add_stats_to_agent_config(agent_cfg)
+    agent = Agent("transformer", agent_cfg, "cuda:0", num_features=3, seed=1)
+    return env, agent, trainer_cfg, tester_cfg, env_cfg
+
+
+def test_stepwise_api_matches_oracle_and_fused_update():
+    """Drive the reference's trainer protocol step by step (act / env.step / store), then check that
+    (a) every env tensor equals the NumPy oracle bit for bit, (b) compute_value_loss / compute_actor_loss agree
+    with the fused device update on the same memory within 1e-3, (c) act-time probs == loss-time probs to 5
+    decimals (agents_test.py:217-220)."""
+    import torch
+    from oracle.env import ResourceV3Oracle
+    env, agent, *_ , env_cfg = _make()
+    state, dec, bin_mask, mha = env.reset()
+    ora = ResourceV3Oracle(env_cfg)
+    ora.load(state)
+    act_probs = []
+    done, t = False, 0
+    while not done:
+        bin_id, feas, probs = agent.act(state, dec, bin_mask, mha, env.build_feasible_mask)
+        o_state, o_dec, o_bm, o_mh = ora.state()
+        assert np.array_equal(feas, ora.build_feasible_mask(o_state, o_dec, o_bm))
+        nstate, ndec, reward, done, info = env.step(bin_id, feas)
+        os_, od_, orw, odone, oinfo = ora.step(np.asarray(bin_id), feas)
+        assert np.array_equal(nstate, os_) and np.array_equal(np.asarray(reward), np.asarray(orw, dtype=np.float32))
+        assert np.array_equal(info["bin_net_mask"], oinfo["bin_net_mask"])
+        assert np.array_equal(info["mha_used_mask"], oinfo["mha_used_mask"]) and done == odone
+        agent.store(state.copy(), dec.copy(), feas.copy(), mha.copy(), bin_id.numpy().copy(), reward.numpy().copy(), t)
+        act_probs.append(np.asarray(probs))
+        state, bin_mask, mha = nstate, info["bin_net_mask"], info["mha_used_mask"]
+        if not done:
+            dec = ndec.copy()
+        t += 1
+    assert t == env.profiles_sample_size
+    R = agent.compute_discounted_rewards(np.zeros((agent.batch_size, 1), np.float32))
+    vloss, values, adv = agent.compute_value_loss(R)
+    total, _, entropy, ploss, probs = agent.compute_actor_loss(agent.bin_actor, agent.bin_masks, agent.bins,
+                                                               agent.actor_decoder_input, adv)
+    np.testing.assert_almost_equal(np.concatenate(act_probs), np.asarray(probs), decimal=5)
+    bufs = agent.memory_to_device()
+    losses = agent.update(bufs).cpu().numpy()
+    ref = np.array([vloss, np.mean(ploss), total, np.mean(entropy)], dtype=np.float64)
+    assert np.all(np.abs(losses - ref) <= 1e-3 * np.maximum(1.0, np.abs(ref))), (losses, ref)
+
+
+def test_trainer_and_tester_run(tmp_path):
+    from tpc_b200.tester import test as tester
+    from tpc_b200.trainer import trainer
+    env, agent, trainer_cfg, tester_cfg, _ = _make(batch=16, nodes=5, rules=8)
+    trainer_cfg = dict(trainer_cfg, n_iterations=3)
+    before = agent.bin_actor.get_flat()
+    out = trainer(env, agent, trainer_cfg, False, str(tmp_path))
+    assert len(out) == 7 and all(len(x) == 3 for x in out)
+    assert all(np.isfinite(v) for buf in out for v in buf)
+    assert not np.array_equal(before, agent.bin_actor.get_flat())          # weights moved
+    path = os.path.join(str(tmp_path), "model", "actor.npz")
+    assert os.path.exists(path)                                            # trainer.py:178-184
+    saved = agent.bin_actor.get_flat()
+    agent.init_weights(5)
+    agent.load_weights(os.path.join(str(tmp_path), "model", "actor"))
+    assert np.array_equal(saved, agent.bin_actor.get_flat())
+    tcfg = json.loads(json.dumps(tester_cfg))
+    tcfg["batch_size"] = 4
+    tcfg["show_per_test_stats"] = False
+    tcfg["testbed"].update(num_tests=1, node_sample_configs={"min": 5, "max": 10, "step": 5},
+                           request_sample_configs={"min": 10, "max": 20, "step": 10})
+    dominant, rejected = tester(env, agent, tcfg, str(tmp_path))
+    assert dominant.shape == rejected.shape == (2 * 2 * 4,)
+    assert os.path.exists(os.path.join(str(tmp_path), "tests", "test.csv"))
+
+
+@pytest.mark.parametrize("reward", ["greedy", "reduced_node_usage"])
+def test_full_size_rollout_properties(reward):
+    """BASELINE full size (batch 1024, 50 nodes x 100 rules): size-independent invariants of a greedy rollout."""
+    import torch
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import ResourceEnvironmentV3
+    agent_cfg, _, env_cfg, _, _, _ = get_configs("ResourceV3", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=1024, node_sample_size=50, profiles_sample_size=100)
+    env_cfg["reward"]["type"] = reward
+    env = ResourceEnvironmentV3("ResourceV3", env_cfg, "cuda:0")
+    env.add_stats_to_agent_config(agent_cfg)
+    agent = Agent("transformer", agent_cfg, "cuda:0", num_features=3, seed=2)
+    bufs = env.device_buffers(store=True)
+    env.reset_into(bufs)
+    init = bufs.batch.clone()
+    agent.rollout(env, bufs, greedy=True)
+    torch.cuda.synchronize()
+    N, R, B = 51, 100, 1024
+    k0 = torch.round(init * 100).long()
+    k1 = torch.round(bufs.batch * 100).long()
+    acts = bufs.actions.long()                                  # (T,B)
+    assert int(acts.min()) >= 0 and int(acts.max()) < N          # only node positions are ever picked
+    assert torch.all(bufs.ptr_masks.gather(2, acts.unsqueeze(2)).squeeze(2) == 0)   # never a masked position
+    assert torch.all(k1[:, 1:N] >= 0)                            # no node is ever overloaded
+    assert torch.equal(k1[:, N:], k0[:, N:]) and torch.all(bufs.batch[:, 0] == -2)   # rules and EOS row untouched
+    # conservation in integer hundredths: capacity removed from node n == sum of the demands placed on it
+    placed = torch.zeros(B, N, 3, dtype=torch.long, device="cuda:0")
+    demands = k0[:, N:, :].permute(1, 0, 2)                     # (T,B,3)
+    placed.scatter_add_(1, acts.t().unsqueeze(2).expand(B, R, 3), demands.permute(1, 0, 2))
+    assert torch.equal((k0 - k1)[:, 1:N], placed[:, 1:N])
+    assert torch.all(bufs.mha_mask[:, N:] == 1)                  # every rule consumed exactly once
+    if reward == "greedy":
+        rejected = (acts == 0).sum(0)
+        assert torch.equal(bufs.rewards.sum(1), (R - rejected).float())

@@ -1,0 +1,80 @@
+"""CPU-side checks of the product package: the C-ABI library loads and exports every symbol include/tpc.h
+declares (no compute calls without a GPU), config plumbing, and that the product never imports the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tpc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tpc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tpc_b200 import build, lib as L
+    path = build.build()
+    so = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    missing = [s for s in declared if not hasattr(so, s)]
+    assert not missing, missing
+    assert sorted(L.SIGNATURES) == declared, set(L.SIGNATURES) ^ set(declared)
+
+
+def test_struct_layouts_match_header():
+    from tpc_b200 import lib as L
+    assert ctypes.sizeof(L.ModelConfig) == 16 * 4
+    assert ctypes.sizeof(L.EnvConfig) == 15 * 4
+    assert ctypes.sizeof(L.RolloutBuffers) == 12 * 8
+    assert ctypes.sizeof(L.A2CHyper) == 5 * 4
+
+
+def test_get_configs_matches_reference_signature():
+    from tpc_b200.configs import get_configs
+    agent, trainer, env, tester, tuner, everything = get_configs("ResourceV3", "tpc")
+    assert agent["actor"]["num_layers"] == 1 and agent["critic"]["inner_layer_dim"] == 512
+    assert env["node_sample_size"] == 10 and env["profiles_sample_size"] == 20 and env["batch_size"] == 128
+    assert trainer["n_steps_to_update"] == 30 and tuner == {}
+    assert get_configs("ResourceV3", "no_such_agent") is None      # configs/configs.py:13-15 prints and returns None
+    agent2, *_ = get_configs("KnapsackV2", "tpc")
+    assert agent2["actor"]["clipnorm"] is None
+
+
+def test_model_and_env_config_translation():
+    from tpc_b200.configs import get_configs
+    from tpc_b200.engine import env_config_struct, model_config_from_agent_config
+    agent, _, env, _, _, _ = get_configs("ResourceV3", "tpc")
+    agent.update(num_bins=11, num_resources=20, tensor_size=31, batch_size=128,
+                 encoder_embedding={"common": True, "num_bin_features": None, "num_resource_features": None})
+    mc = model_config_from_agent_config(agent, 3)
+    assert (mc.actor_num_layers, mc.critic_num_layers, mc.dim_model, mc.num_heads) == (1, 3, 128, 8)
+    assert mc.has_logit_clipping == 1 and mc.logit_clipping_C == 10.0 and mc.common_embedding == 1
+    e = env_config_struct(env, 0)
+    assert (e.reward_type, e.num_profiles, e.node_max_val, e.req_max_val, e.mask_nodes_in_mha) == (0, 1000, 100, 30, 1)
+    env["reward"]["type"] = "reduced_node_usage"
+    e = env_config_struct(env, 0)
+    assert e.reward_type == 3 and e.rejection_penalty == -2.0 and e.use_new_node_penalty == -1.0
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "transformer-pointer-critic_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tpc_b200 import lib as L
+    from tpc_b200.engine import Engine
+    with pytest.raises(L.TpcError):
+        Engine(L.ModelConfig(), "cuda:0")
