@@ -45,6 +45,25 @@ __device__ __forceinline__ void load_a_frag(const float* __restrict__ base, int 
   a[3] = fbits(base[(size_t)rb * ld + c0 + t + 4] * scale);
 }
 
+// A masked key contributes exp(-1e9 - max) == 0 exactly in fp32, so 8-key tiles without any unmasked
+// key are skipped: exact, and during an episode a third to a half of the keys (placed rules, full nodes) are masked.
+// If nothing is unmasked (cannot happen on the reference's trajectories) every tile stays live and the arithmetic
+// degenerates to the reference's uniform softmax over equal -1e9 logits.
+__device__ __forceinline__ void mark_live_tiles(const float* Ms, int* live, int ntiles) {
+  __shared__ int any_live;
+  if (threadIdx.x == 0) any_live = 0;
+  __syncthreads();
+  for (int nt = threadIdx.x; nt < ntiles; nt += blockDim.x) {
+    int l = 0;
+    for (int j = 0; j < 8; ++j) l |= (Ms[nt * 8 + j] == 0.f);
+    live[nt] = l;
+    if (l) any_live = 1;
+  }
+  __syncthreads();
+  if (!any_live)
+    for (int nt = threadIdx.x; nt < ntiles; nt += blockDim.x) live[nt] = 1;
+}
+
 // Forward: 16 warps per state; head h is shared by warps h and h+8 (alternating 16-row query blocks).
 // Two passes over the keys keep the register footprint small: pass 1 finds the row maximum (plain TF32),
 // pass 2 recomputes the scores in 3xTF32 (hi/lo split of Q and K: fp32-level logits, the softmax amplifies
@@ -58,12 +77,15 @@ __global__ void __launch_bounds__(512) attn_fwd_kernel(const float* __restrict__
   float* Ks = sm;
   float* Vs = Ks + Lp * KS;
   float* Ms = Vs + Lp * KS;  // additive key mask: mask * -1e9, -inf beyond L
+  int* live = reinterpret_cast<int*>(Ms + Lp);   // [ntiles] 1 if the 8-key tile holds an unmasked key
   const int c = blockIdx.x;
   const float* base = qkv + (size_t)c * L * 384;
   stage_rows(base, 384, 128, L, Lp, Ks);
   stage_rows(base, 384, 256, L, Lp, Vs);
   for (int j = threadIdx.x; j < Lp; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
+  __syncthreads();
+  mark_live_tiles(Ms, live, ntiles);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -87,6 +109,7 @@ __global__ void __launch_bounds__(512) attn_fwd_kernel(const float* __restrict__
     // ---- pass 1: row maxima
     float mx0 = -INFINITY, mx1 = -INFINITY;
     for (int nt = 0; nt < ntiles; ++nt) {
+      if (!live[nt]) continue;
       float s[4] = {0.f, 0.f, 0.f, 0.f};
       const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
       mma_tf32(s, qh[0][0], qh[0][1], qh[0][2], qh[0][3], tfbits(kr[0]), tfbits(kr[4]));
@@ -102,8 +125,8 @@ __global__ void __launch_bounds__(512) attn_fwd_kernel(const float* __restrict__
     // ---- pass 2: exact scores, softmax numerators, P.V
     float sum0 = 0.f, sum1 = 0.f;
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 2
     for (int nt = 0; nt < ntiles; ++nt) {
+      if (!live[nt]) continue;
       float s[4] = {0.f, 0.f, 0.f, 0.f};
       const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
 #pragma unroll
@@ -179,6 +202,7 @@ __global__ void __launch_bounds__(512) attn_bwd_kernel(const float* __restrict__
   float* Ms = B_s + Lp * KS;       // [Lp]
   float* Ls = Ms + Lp;             // [8][Lp] log-sum-exp
   float* Ds = Ls + 8 * Lp;         // [8][Lp]
+  int* live = reinterpret_cast<int*>(Ds + 8 * Lp);   // [ntiles]
   const int c = blockIdx.x;
   const float* base = qkv + (size_t)c * L * 384;
   const float* obase = att + (size_t)c * L * 128;
@@ -208,6 +232,8 @@ __global__ void __launch_bounds__(512) attn_bwd_kernel(const float* __restrict__
     Ls[h * Lp + i] = l;
   }
   __syncthreads();
+  mark_live_tiles(Ms, live, ntiles);
+  __syncthreads();
 
   // ---------------- phase A: dQ ----------------
   for (int r0 = sub * 16; r0 < L; r0 += 32) {
@@ -221,8 +247,8 @@ __global__ void __launch_bounds__(512) attn_bwd_kernel(const float* __restrict__
     const float la = Ls[h * Lp + ia], lb = Ls[h * Lp + ib];
     const float Da = Ds[h * Lp + ia], Db = Ds[h * Lp + ib];
     float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 2
     for (int nt = 0; nt < ntiles; ++nt) {
+      if (!live[nt]) continue;     // masked keys: P == 0 exactly, no contribution to dQ
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
       const float* kr = A_s + (nt * 8 + g) * KS + hc + t;
       const float* vr = B_s + (nt * 8 + g) * KS + hc + t;
@@ -268,8 +294,9 @@ __global__ void __launch_bounds__(512) attn_bwd_kernel(const float* __restrict__
     const float ma = ja < L ? Ms[ja] : -INFINITY, mb = jb < L ? Ms[jb] : -INFINITY;
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 2
-    for (int it = 0; it < ntiles; ++it) {
+    // both 8-key tiles of this block masked: dK = dV = 0 (still written below)
+    const bool dead = !live[j0 >> 3] && !(((j0 >> 3) + 1 < ntiles) && live[(j0 >> 3) + 1]);
+    for (int it = 0; it < (dead ? 0 : ntiles); ++it) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
       const float* qr = A_s + (it * 8 + g) * KS + hc + t;
       const float* dr = B_s + (it * 8 + g) * KS + hc + t;
@@ -317,11 +344,11 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 208) return TPC_ERR_SHAPE;
   const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(2 * Lp * KS + Lp) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  const size_t smem = (size_t)(2 * Lp * KS + Lp + Lp / 8 + 8) * sizeof(float);
+  static size_t attr_smem = 0;   // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
+  if (smem > attr_smem) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
   attn_fwd_kernel<<<C, 512, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
   TPC_CHECK_LAUNCH();
@@ -333,11 +360,11 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 200) return TPC_ERR_SHAPE;
   const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(2 * Lp * KS + 17 * Lp) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  const size_t smem = (size_t)(2 * Lp * KS + 17 * Lp + Lp / 8 + 8) * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
   attn_bwd_kernel<<<C, 512, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
   TPC_CHECK_LAUNCH();

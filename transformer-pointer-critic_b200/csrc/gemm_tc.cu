@@ -488,9 +488,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         if (row < g.Kin) {
+          if (c * 32 + 32 <= ncols && (g.ld[nj] & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < ncols) atomicAdd(dst + c * 32 + j, v[j]);
+            for (int j = 0; j < 32; j += 4)   // 16-byte vector reduction (sm_90+): 4x fewer L2 atomic ops
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + j), "f"(v[j]),
+                           "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < ncols) atomicAdd(dst + c * 32 + j, v[j]);
+          }
         }
       }
       if (ki == 0 && g.bias[nj] != nullptr && q == 0) {
@@ -643,8 +651,9 @@ int launch_wgrad(TmapCache* tc, const float* X, int ldx, const float* dY, int ld
   g.nj_tiles = ceil_div(Nout, 128);
   if (g.nj_tiles > 4) return TPC_ERR_SHAPE;
   const int out_tiles = g.ki_tiles * g.nj_tiles;
-  // enough token splits to fill the machine, at least 256 tokens (8 stages) per split
-  int splits = ceil_div(2 * num_sms, out_tiles);
+  // one work item per SM (each item ends with 16 K atomic adds onto the same addresses: more splits only add
+  // contention), at least 256 tokens (8 stages) per split
+  int splits = num_sms / out_tiles;
   const int max_splits = ceil_div(M, 256);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
