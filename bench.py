@@ -197,7 +197,9 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    chunk = args.chunk or 2048
+    n_states = B * T
+    pieces = (n_states + 10239) // 10240
+    chunk = args.chunk or -(-n_states // pieces)
     M, Kd = chunk * S, 128
     A = torch.randn(M, Kd, device=dev)
     W = torch.randn(128, Kd, device=dev)
@@ -263,7 +265,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default 1024)")
     ap.add_argument("--nodes", type=int, default=WORKLOAD["nodes"])
     ap.add_argument("--rules", type=int, default=WORKLOAD["rules"])
-    ap.add_argument("--chunk", type=int, default=0, help="states per update chunk (default 2048)")
+    ap.add_argument("--chunk", type=int, default=0, help="states per update chunk (default: ~10240, equal chunks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -66,6 +66,40 @@ def main():
         print(f"gemm3x M={M} N={N} K={K}: rel-max err {err:.3e}")
         assert err < (2e-5 if K <= 512 else 3e-4), err  # long-K: fp32 accumulation order inside the tensor core
 
+    # weight-resident kernel (K == 128, many row tiles): 1-pass and 3xTF32, bias + relu, aux add / gate
+    for (M, N) in [(40000, 128), (39999, 384), (40001, 512)]:
+        K = 128
+        A = torch.randn(M, K, device=dev)
+        Bt = torch.randn(N, K, device=dev) / K ** 0.5
+        Blo = Bt - (Bt.view(torch.int32) & -8192).view(torch.float32)
+        bias = torch.randn(N, device=dev)
+        aux = torch.randn(M, N, device=dev)
+        ref0 = A.double() @ Bt.double().T
+        for split in (False, True):
+            D = torch.full((M, N), float("nan"), device=dev)
+            rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, ptr(bias), None, 0, 0, None, None, None, 1, 1,
+                              ptr(Blo) if split else None, stream)
+            assert rc == 0, rc
+            torch.cuda.synchronize()
+            ref = torch.relu(ref0 + bias.double())
+            err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+            print(f"bres M={M} N={N} split={split} bias+relu: {err:.3e}")
+            assert err < (2e-5 if split else 2e-3), err
+        D = torch.full((M, N), float("nan"), device=dev)
+        rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, ptr(aux), N, 1, None, None, None, 4, 1, None, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        err = (D.double() - (ref0 + aux.double())).abs().max().item() / ref0.abs().max().item()
+        print(f"bres M={M} N={N} aux add: {err:.3e}")
+        assert err < 2e-3, err
+        D = aux.clone()
+        rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, None, ptr(D), N, 2, None, None, None, 4, 1, None, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        err = (D.double() - ref0 * (aux.double() > 0)).abs().max().item() / ref0.abs().max().item()
+        print(f"bres M={M} N={N} gate in place: {err:.3e}")
+        assert err < 2e-3, err
+
     # relu + aux add + round
     M, N, K = 555, 256, 128
     A = torch.randn(M, K, device=dev)

@@ -26,8 +26,12 @@ def reset(ep):
 for it in range(int(os.environ.get("ITERS", 3))):
     e0, e1, e2, e3 = ev(), ev(), ev(), ev()
     reset(it)
+    torch.cuda.synchronize(); h0 = time.perf_counter()
     e0.record(); eng.rollout(e, bufs, False, 5, 0, it); e1.record()
+    h1 = time.perf_counter()
     eng.a2c_grads(bufs, 0.99, 1.0, 0.01, chunk_states=chunk); e2.record()
+    h2 = time.perf_counter()
+    print(f"   host launch time: rollout {1e3*(h1-h0):.1f} ms, a2c {1e3*(h2-h1):.1f} ms")
     eng.adam_apply(0, 1e-4, 1.0); eng.adam_apply(1, 5e-4, 1.0); e3.record()
     torch.cuda.synchronize()
     tr, tu, ta = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)

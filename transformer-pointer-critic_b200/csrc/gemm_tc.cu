@@ -350,6 +350,281 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Weight-resident variant for K == 128 (every 128-wide projection): a CTA owns ONE 128-column tile of the output,
+// loads that slice of the weights (64 KB, + 64 KB low parts in 3xTF32 mode) into shared memory once and then only
+// streams activation tiles. The generic kernel re-reads the weight tile from L2 for every 128-row tile, which at
+// these shapes is 1/3 to 1/2 of all L2->SM traffic (ncu: L2-bound at ~60 % of the HBM rate). CTAs that own
+// different column tiles of the same rows run side by side, so the activation tile comes from HBM once.
+// Epilogue: bias / ReLU / aux add / aux ReLU-gate / TF32 rounding (no LayerNorm, no split-K: generic kernel).
+// ---------------------------------------------------------------------------------------------------------
+template <bool SPLIT>
+struct Bres {
+  static constexpr int NKB = 4;                                  // K = 128 = 4 k-blocks of 32
+  static constexpr int B_KB_BYTES = (SPLIT ? 2 : 1) * TILE_BYTES; // hi (+ lo) of one k-block
+  static constexpr int B_BYTES = NKB * B_KB_BYTES;               // 64 KB / 128 KB
+  static constexpr int ASTAGES = SPLIT ? 4 : 6;                  // 16 KB activation k-blocks in flight
+  static constexpr int EPI_COLS = SPLIT ? 64 : 128;              // staging tile: half / full width
+  static constexpr int EPI_B = BM * EPI_COLS * 4;
+  static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + 256 + 1024;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
+                 const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
+  using C = Bres<SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bsm = smem;
+  uint8_t* ring = smem + C::B_BYTES;
+  uint8_t* epi = ring + C::ASTAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::EPI_B);
+  uint64_t* full = bars;                        // [ASTAGES]
+  uint64_t* empty = full + C::ASTAGES;          // [ASTAGES]
+  uint64_t* lofull = empty + C::ASTAGES;        // [ASTAGES]
+  uint64_t* tfull = lofull + C::ASTAGES;        // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint64_t* auxfull = tempty + 2;               // [1]
+  uint64_t* bfull = auxfull + 1;                // [1] weights resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (SPLIT) tma_prefetch_desc(&tmBlo);
+    if (g.aux_mode) tma_prefetch_desc(&tmAux);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < C::ASTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&lofull[s], 4);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_init(auxfull, 1);
+    mbar_init(bfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA: column tile n_t, row tiles m0, m0 + groups, ...
+  const int n_t = blockIdx.x % g.n_tiles;
+  const int groups = gridDim.x / g.n_tiles;
+  const int m0 = blockIdx.x / g.n_tiles;
+  const int m_tiles = (g.M + BM - 1) / BM;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(bfull, C::B_BYTES);
+      for (int kb = 0; kb < C::NKB; ++kb) {
+        tma_load_2d(bsm + kb * C::B_KB_BYTES, &tmB, bfull, kb * BK, n_t * BN);
+        if (SPLIT) tma_load_2d(bsm + kb * C::B_KB_BYTES + TILE_BYTES, &tmBlo, bfull, kb * BK, n_t * BN);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_t = m0; m_t < m_tiles; m_t += groups) {
+        for (int kb = 0; kb < C::NKB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], TILE_BYTES);
+          tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, m_t * BM);
+          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    if (SPLIT) {
+      const int row = threadIdx.x;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_t = m0; m_t < m_tiles; m_t += groups) {
+        for (int kb = 0; kb < C::NKB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          const uint8_t* sa = ring + stage * TILE_BYTES + row * 128;
+          float lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
+            lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
+            lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
+          }
+          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+      mbar_wait(bfull, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < C::NKB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (SPLIT) mbar_wait(&lofull[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + stage * TILE_BYTES), 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES), 16, 1024);
+          const uint64_t dbl = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES + TILE_BYTES), 16, 1024);
+          const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_tf32_ss(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1u);
+              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const bool leader = (et == 0);
+    uint32_t aux_phase = 0;
+    constexpr int NPASS = 128 / C::EPI_COLS;          // 1 (full staging tile) or 2 (half)
+    constexpr int BOXES = C::EPI_COLS / BK;           // TMA boxes per pass
+    if (!SPLIT && g.aux_mode && leader && m0 < m_tiles) {
+      mbar_expect_tx(auxfull, EPI_BYTES);
+      for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, m0 * BM);
+    }
+    int it = 0;
+    if (g.aux_mode == 0) {
+      // Streaming epilogue: every 32-column chunk goes through its own 16 KB staging box and is stored by TMA
+      // right away; boxes form a ring of NBUF, so the store of chunk c overlaps the TMEM load / math of chunk c+1.
+      constexpr int NBUF = C::EPI_B / TILE_BYTES;       // 2 (3xTF32) or 4
+      int cidx = 0;
+      for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c, ++cidx) {
+          uint8_t* box = epi + (cidx % NBUF) * TILE_BYTES;
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          if (c == 3) {                                   // accumulator drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            if (g.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c * 8 + j4);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+            *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
+          }
+          // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
+          // older stores may still be in flight when the threads are released
+          if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 2) : "memory");
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
+            tma_store_commit();
+          }
+        }
+      }
+      if (leader) tma_store_wait_all0();
+    } else {
+      for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        if (!SPLIT && g.aux_mode) {
+          mbar_wait(auxfull, aux_phase);
+          aux_phase ^= 1;
+        }
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+  #pragma unroll 1
+        for (int pass = 0; pass < NPASS; ++pass) {
+  #pragma unroll 1
+          for (int cc = 0; cc < BOXES; ++cc) {
+            const int c = pass * BOXES + cc;          // 32-column chunk of the accumulator
+            float v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+  #pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int c4g = c * 8 + j4;               // global float4 column of the tile
+              const int c4s = cc * 8 + j4;              // float4 column inside the staging tile
+              float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+              if (g.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c4g);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (!SPLIT && g.aux_mode) {
+                const float4 a = *reinterpret_cast<const float4*>(epi + epi_off(et, c4s));
+                if (g.aux_mode == 1) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                else { o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f; }
+              }
+              if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+              *reinterpret_cast<float4*>(epi + epi_off(et, c4s)) = o;
+            }
+          }
+          if (pass == NPASS - 1) {                      // accumulator fully drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            for (int j = 0; j < BOXES; ++j)
+              tma_store_2d(&tmD, epi + j * TILE_BYTES, n_t * BN + (pass * BOXES + j) * BK, m_t * BM);
+            tma_store_commit();
+            tma_store_wait_read0();
+            const int next = m_t + groups;
+            if (!SPLIT && g.aux_mode && next < m_tiles) {
+              mbar_expect_tx(auxfull, EPI_BYTES);
+              for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, next * BM);
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+      if (leader) tma_store_wait_all0();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Weight gradient: D[Kin-tile 128][Nout-tile 128] += sum over tokens of X[t][ki*128+i] * dY[t][nj*128+j]
 // Operands are the raw row-major activation tiles (token rows of 128 B per 32-feature box) consumed as
 // MN-major UMMA operands: LBO = distance between 32-feature boxes, 8 tokens (two 4-token swizzle atoms) per MMA.
@@ -557,6 +832,10 @@ int gemm_tc_init() {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_bres_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_bres_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) {
       fprintf(stderr, "[tpc] cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e));
@@ -633,6 +912,17 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     TPC_TRY(get_tmap(tc, epi.aux, M, N, epi.ldaux, BM, 0, &tAux));
   } else {
     tAux = tD;
+  }
+  // weight-resident kernel: K == 128, no LayerNorm / split-K, (3xTF32: no aux), enough row tiles per CTA
+  const int m_tiles = ceil_div(M, BM);
+  const bool bres = (K == 128) && !epi.ln && !epi.atomic && !(g.split && epi.aux_mode) && g.n_tiles <= num_sms &&
+                    m_tiles * g.n_tiles >= 2 * num_sms;
+  if (bres) {
+    int grid = (num_sms / g.n_tiles) * g.n_tiles;
+    if (g.split) gemm_bres_kernel<true><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else gemm_bres_kernel<false><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    TPC_CHECK_LAUNCH();
+    return TPC_OK;
   }
   const int grid = g.num_items < num_sms ? g.num_items : num_sms;
   gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);

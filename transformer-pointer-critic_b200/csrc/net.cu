@@ -439,7 +439,13 @@ int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_p
   cudaStream_t st = (cudaStream_t)stream;
   const int S = N + R, T = R, F = m->cfg.dec_features;
   const long long n = (long long)T * B;
-  int chunk = hp->chunk_states > 0 ? hp->chunk_states : 2048;
+  // default: ~10 k states per chunk, all chunks equal (fewer, fuller launches: 1.68 s -> 1.52 s per update at the
+  // headline shape vs 2 k chunks); ~5.8 MB of saved activations per state for the 9-layer critic
+  int chunk = hp->chunk_states;
+  if (chunk <= 0) {
+    const long long pieces = (n + 10239) / 10240;
+    chunk = (int)((n + pieces - 1) / pieces);
+  }
   if (chunk > n) chunk = (int)n;
   const float inv_total = 1.0f / (float)(hp->total_states > 0 ? hp->total_states : n);
   float* Rt = ar.f((size_t)n);
