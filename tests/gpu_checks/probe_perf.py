@@ -10,7 +10,7 @@ from tests.gpu_checks.check_model import make_cfg
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", 1024)); N, R, F = 51, 100, 3
-chunk = int(os.environ.get("CHUNK", 2048))
+chunk = int(os.environ.get("CHUNK", 10240))
 cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "env_rv3_shipped_greedy.json")))
 mc, ca, cc = make_cfg(N, R)
 eng = Engine(mc, dev)

@@ -125,3 +125,37 @@ def test_full_size_rollout_properties(reward):
     if reward == "greedy":
         rejected = (acts == 0).sum(0)
         assert torch.equal(bufs.rewards.sum(1), (R - rejected).float())
+
+
+def test_knapsack_v2_trains_on_the_same_kernels(tmp_path):
+    """BASELINE config #4: configs/KnapsackV2.json (2 features, separate embeddings, clipnorm null)."""
+    import torch
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import KnapsackEnvironmentV2
+    from tpc_b200.trainer import trainer
+    from oracle.env import KnapsackV2Oracle
+    agent_cfg, trainer_cfg, env_cfg, _, _, _ = get_configs("KnapsackV2", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=32, bin_sample_size=5, item_sample_size=8)
+    env = KnapsackEnvironmentV2("KnapsackV2", env_cfg, "cuda:0")
+    env.add_stats_to_agent_config(agent_cfg)
+    agent = Agent("transformer", agent_cfg, "cuda:0", num_features=2, seed=3)
+    # one greedy rollout replayed through the NumPy oracle: bit-exact bookkeeping and rewards
+    bufs = env.device_buffers(store=True)
+    env.reset_into(bufs)
+    init = bufs.batch.cpu().numpy().copy()
+    agent.rollout(env, bufs, greedy=True)
+    torch.cuda.synchronize()
+    ora = KnapsackV2Oracle(env_cfg)
+    state, dec, bm, mh = ora.load(init)
+    acts = bufs.actions.cpu().numpy()
+    for t in range(env.profiles_sample_size):
+        feas = ora.build_feasible_mask(state, dec, bm)
+        assert np.array_equal(bufs.ptr_masks[t].cpu().numpy(), feas)
+        state, dec, rw, done, info = ora.step(acts[t], feas)
+        assert np.array_equal(bufs.rewards[:, t].cpu().numpy(), np.asarray(rw, dtype=np.float32).reshape(-1))
+        bm, mh = info["bin_net_mask"], info["mha_used_mask"]
+    assert done and np.array_equal(bufs.batch.cpu().numpy(), state)
+    out = trainer(env, agent, dict(trainer_cfg, n_iterations=2), False, str(tmp_path))
+    assert all(np.isfinite(v) for buf in out for v in buf)

@@ -23,6 +23,15 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t fbits(float x) { return __float_as_uint(x); }
+// 2^x on the SFU without the denormal fix-up sequence of exp2f/__expf (inputs <= 0 here, tiny results flush to 0)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float QSCALE = 0.25f * LOG2E;   // 1/sqrt(depth=16), scores kept in log2 units so that exp == one ex2
 __device__ __forceinline__ uint32_t tfbits(float x) { return __float_as_uint(tf32_rn(x)); }
 
 // stage the 16 columns of one head (at column offset col0 of a [rows][ld] matrix) of L rows into smem [Lp][KS]
@@ -63,6 +72,19 @@ __device__ __forceinline__ void mark_live_tiles(const float* Ms, int* live, int 
   if (!any_live)
     for (int nt = threadIdx.x; nt < ntiles; nt += blockDim.x) live[nt] = 1;
 }
+// the flags as a register bit mask (tile nt -> bit nt); beyond 64 tiles (L > 512) nothing is skipped
+struct LiveBits {
+  unsigned long long w;
+  __device__ __forceinline__ void load(const int* live, int ntiles) {
+    w = ~0ull;
+    if (ntiles <= 64) {
+      w = 0ull;
+      for (int nt = 0; nt < ntiles; ++nt)
+        if (live[nt]) w |= 1ull << nt;
+    }
+  }
+  __device__ __forceinline__ bool test(int nt) const { return nt >= 64 || ((w >> nt) & 1ull); }
+};
 
 // Forward: one CTA of 4 warps per (state, head) -- ~26 KB of smem at 151 tokens, so 8 CTAs share an SM and one
 // CTA's staging latency hides behind the others' math; the warps take alternating 16-row query blocks.
@@ -93,12 +115,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const bool pv3x = L < 64;
+  LiveBits lb;
+  lb.load(live, ntiles);
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
     uint32_t qh[2][4], ql[2][4];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       uint32_t raw[4];
-      load_a_frag(base, 384, r0, L, hg + kk * 8, g, t, 0.25f, raw);   // 1/sqrt(depth=16), exact in fp32
+      load_a_frag(base, 384, r0, L, hg + kk * 8, g, t, QSCALE, raw);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float x = __uint_as_float(raw[i]);
@@ -110,7 +134,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
     // ---- pass 1: row maxima
     float mx0 = -INFINITY, mx1 = -INFINITY;
     for (int nt = 0; nt < ntiles; ++nt) {
-      if (!live[nt]) continue;
+      if (!lb.test(nt)) continue;
       float s[4] = {0.f, 0.f, 0.f, 0.f};
       const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
       mma_tf32(s, qh[0][0], qh[0][1], qh[0][2], qh[0][3], tfbits(kr[0]), tfbits(kr[4]));
@@ -127,8 +151,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
     float sum0 = 0.f, sum1 = 0.f;
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int nt = 0; nt < ntiles; ++nt) {
-      if (!live[nt]) continue;
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!lb.test(nt)) continue;
+      float s[4] = {-mx0, -mx0, -mx1, -mx1};     // accumulate score - rowmax directly
       const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
@@ -141,8 +165,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
         mma_tf32(s, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], b0h, b1h);
       }
       const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-      const float p0 = __expf(s[0] + ma - mx0), p1 = __expf(s[1] + mb - mx0);
-      const float p2 = __expf(s[2] + ma - mx1), p3 = __expf(s[3] + mb - mx1);
+      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + mb);
+      const float p2 = ex2(s[2] + ma), p3 = ex2(s[3] + mb);
       sum0 += p0 + p1;
       sum1 += p2 + p3;
       // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
@@ -172,13 +196,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
       float* dst = att + ((size_t)c * L + ra) * 128 + hg + 2 * t;
       *reinterpret_cast<float2*>(dst) = make_float2(o[0][0] * i0, o[0][1] * i0);
       *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][0] * i0, o[1][1] * i0);
-      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 + logf(sum0);
+      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 * LN2 + logf(sum0);   // natural-log units
     }
     if (rb < L) {
       float* dst = att + ((size_t)c * L + rb) * 128 + hg + 2 * t;
       *reinterpret_cast<float2*>(dst) = make_float2(o[0][2] * i1, o[0][3] * i1);
       *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][2] * i1, o[1][3] * i1);
-      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 + logf(sum1);
+      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 * LN2 + logf(sum1);
     }
   }
 }
@@ -218,7 +242,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   for (int j = threadIdx.x; j < Lp; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   for (int i = threadIdx.x; i < Lp; i += blockDim.x) {
-    float d = 0.f, l = 0.f;
+    float d = 0.f, l = INFINITY;   // padded queries: exp2(score - inf) == 0
     if (i < L) {
       const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hg);
       const float4* dp = reinterpret_cast<const float4*>(dobase + (size_t)i * 128 + hg);
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
         const float4 a = op[q], b = dp[q];
         d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
       }
-      l = lse[((size_t)c * L + i) * 8 + h];
+      l = lse[((size_t)c * L + i) * 8 + h] * LOG2E;   // log2 units, like the recomputed scores
     }
     Ds[i] = d;
     Ls[i] = l;
@@ -235,12 +259,14 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   __syncthreads();
   mark_live_tiles(Ms, live, ntiles);
   __syncthreads();
+  LiveBits lbits;
+  lbits.load(live, ntiles);
 
   // ---------------- phase A: dQ ----------------
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
     uint32_t qa[2][4], da[2][4];
-    load_a_frag(base, 384, r0, L, hg, g, t, 0.25f, qa[0]);
-    load_a_frag(base, 384, r0, L, hg + 8, g, t, 0.25f, qa[1]);
+    load_a_frag(base, 384, r0, L, hg, g, t, QSCALE, qa[0]);
+    load_a_frag(base, 384, r0, L, hg + 8, g, t, QSCALE, qa[1]);
     load_a_frag(dobase, 128, r0, L, hg, g, t, 1.f, da[0]);
     load_a_frag(dobase, 128, r0, L, hg + 8, g, t, 1.f, da[1]);
     round_frag(qa[0]); round_frag(qa[1]); round_frag(da[0]); round_frag(da[1]);
@@ -249,8 +275,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     const float Da = Ds[ia], Db = Ds[ib];
     float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int nt = 0; nt < ntiles; ++nt) {
-      if (!live[nt]) continue;     // masked keys: P == 0 exactly, no contribution to dQ
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!lbits.test(nt)) continue;     // masked keys: P == 0 exactly, no contribution to dQ
+      // accumulators start at the row constants: s = score - lse (log2 units), dp = dO.V^T - D
+      float s[4] = {-la, -la, -lb, -lb}, dp[4] = {-Da, -Da, -Db, -Db};
       const float* kr = A_s + (nt * 8 + g) * KS + hc + t;
       const float* vr = B_s + (nt * 8 + g) * KS + hc + t;
       mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], tfbits(kr[0]), tfbits(kr[4]));
@@ -258,10 +285,10 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
       mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], tfbits(vr[0]), tfbits(vr[4]));
       mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], tfbits(vr[8]), tfbits(vr[12]));
       const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-      const float p0 = __expf(s[0] + ma - la), p1 = __expf(s[1] + mb - la);
-      const float p2 = __expf(s[2] + ma - lb), p3 = __expf(s[3] + mb - lb);
-      const uint32_t a0 = tfbits(p0 * (dp[0] - Da)), a2 = tfbits(p1 * (dp[1] - Da));
-      const uint32_t a1 = tfbits(p2 * (dp[2] - Db)), a3 = tfbits(p3 * (dp[3] - Db));
+      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + mb);
+      const float p2 = ex2(s[2] + ma), p3 = ex2(s[3] + mb);
+      const uint32_t a0 = tfbits(p0 * dp[0]), a2 = tfbits(p1 * dp[1]);
+      const uint32_t a1 = tfbits(p2 * dp[2]), a3 = tfbits(p3 * dp[3]);
       const float* k0 = A_s + (nt * 8 + 2 * t) * KS + hc + g;
       mma_tf32(dq[0], a0, a1, a2, a3, tfbits(k0[0]), tfbits(k0[KS]));
       mma_tf32(dq[1], a0, a1, a2, a3, tfbits(k0[8]), tfbits(k0[KS + 8]));
@@ -286,8 +313,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   __syncthreads();
   for (int j0 = warp * 16; j0 < L; j0 += 64) {
     uint32_t ka[2][4], va[2][4];
-    load_a_frag(base + 128, 384, j0, L, hg, g, t, 0.25f, ka[0]);
-    load_a_frag(base + 128, 384, j0, L, hg + 8, g, t, 0.25f, ka[1]);
+    load_a_frag(base + 128, 384, j0, L, hg, g, t, QSCALE, ka[0]);
+    load_a_frag(base + 128, 384, j0, L, hg + 8, g, t, QSCALE, ka[1]);
     load_a_frag(base + 256, 384, j0, L, hg, g, t, 1.f, va[0]);
     load_a_frag(base + 256, 384, j0, L, hg + 8, g, t, 1.f, va[1]);
     round_frag(ka[0]); round_frag(ka[1]); round_frag(va[0]); round_frag(va[1]);
@@ -296,24 +323,23 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     // both 8-key tiles of this block masked: dK = dV = 0 (still written below)
-    const bool dead = !live[j0 >> 3] && !(((j0 >> 3) + 1 < ntiles) && live[(j0 >> 3) + 1]);
+    const bool dead = !lbits.test(j0 >> 3) && !(((j0 >> 3) + 1 < ntiles) && lbits.test((j0 >> 3) + 1));
     for (int it = 0; it < (dead ? 0 : ntiles); ++it) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+      const int i0 = it * 8 + 2 * t, i1 = i0 + 1;   // query columns of this thread
+      const float l0 = Ls[i0], l1 = Ls[i1];
+      const float D0 = Ds[i0], D1 = Ds[i1];
+      float s[4] = {-l0, -l1, -l0, -l1}, dp[4] = {-D0, -D1, -D0, -D1};
       const float* qr = A_s + (it * 8 + g) * KS + hc + t;
       const float* dr = B_s + (it * 8 + g) * KS + hc + t;
       mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], tfbits(qr[0]), tfbits(qr[4]));
       mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], tfbits(qr[8]), tfbits(qr[12]));
       mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], tfbits(dr[0]), tfbits(dr[4]));
       mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], tfbits(dr[8]), tfbits(dr[12]));
-      const int i0 = it * 8 + 2 * t, i1 = i0 + 1;   // query columns of this thread
-      const bool v0 = i0 < L, v1 = i1 < L;
-      const float l0 = Ls[i0], l1 = Ls[i1];
-      const float D0 = Ds[i0], D1 = Ds[i1];
-      const float p0 = v0 ? __expf(s[0] + ma - l0) : 0.f, p1 = v1 ? __expf(s[1] + ma - l1) : 0.f;
-      const float p2 = v0 ? __expf(s[2] + mb - l0) : 0.f, p3 = v1 ? __expf(s[3] + mb - l1) : 0.f;
+      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + ma);
+      const float p2 = ex2(s[2] + mb), p3 = ex2(s[3] + mb);
       const uint32_t pa0 = tfbits(p0), pa2 = tfbits(p1), pa1 = tfbits(p2), pa3 = tfbits(p3);
-      const uint32_t sa0 = tfbits(p0 * (dp[0] - D0)), sa2 = tfbits(p1 * (dp[1] - D1));
-      const uint32_t sa1 = tfbits(p2 * (dp[2] - D0)), sa3 = tfbits(p3 * (dp[3] - D1));
+      const uint32_t sa0 = tfbits(p0 * dp[0]), sa2 = tfbits(p1 * dp[1]);
+      const uint32_t sa1 = tfbits(p2 * dp[2]), sa3 = tfbits(p3 * dp[3]);
       const float* d0 = B_s + (it * 8 + 2 * t) * KS + hc + g;
       const float* q0 = A_s + (it * 8 + 2 * t) * KS + hc + g;
       mma_tf32(dv[0], pa0, pa1, pa2, pa3, tfbits(d0[0]), tfbits(d0[KS]));
