@@ -111,6 +111,14 @@ int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, f
 int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int M,
               int Kin, int Nout, void* stream);
 
+/* self-attention of one encoder stack on packed qkv[C*L][384] (q | k | v), 8 heads x 16; mask[c*mS + m0 + j] != 0
+ * hides key j. Replaces scaled_dot_product_attention + head split/merge (common/attention.py:37-48,
+ * common/utils.py:13-47) and its backward. att[C*L][128], lse[C*L][8] (log-sum-exp, saved for the backward). */
+int tpc_attention_fwd(tpc_handle* h, const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att,
+                      float* lse, void* stream);
+int tpc_attention_bwd(tpc_handle* h, const float* qkv, const float* att, const float* lse, const float* datt,
+                      const float* mask, int mS, int m0, int C, int L, float* dqkv, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * model forward passes (step-wise, API-exact mode used by Agent.act / tests)
  * ---------------------------------------------------------------------------------------------------- */

@@ -32,7 +32,7 @@ __device__ __forceinline__ float ex2(float x) {
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float QSCALE = 0.25f * LOG2E;   // 1/sqrt(depth=16), scores kept in log2 units so that exp == one ex2
-__device__ __forceinline__ uint32_t tfbits(float x) { return __float_as_uint(tf32_rn(x)); }
+__device__ __forceinline__ uint32_t tfbits(float x) { return tf32_rn_bits(x); }   // MMA truncates: add == round
 
 // stage the 16 columns of one head (at column offset col0 of a [rows][ld] matrix) of L rows into smem [Lp][KS]
 __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int ld, int col0, int L, int Lp, float* dst) {
@@ -170,20 +170,24 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
       sum0 += p0 + p1;
       sum1 += p2 + p3;
       // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
-      // 3xTF32 again: with few keys there is no averaging of the operand rounding.
-      const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
-      const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
-      const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
       const float* v0 = Vs + (nt * 8 + 2 * t) * KS + hc + g;
+      if (pv3x) {
+        // short sequences: 3xTF32 again (with few keys there is no averaging of the operand rounding)
+        const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
+        const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
+        const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
 #pragma unroll
-      for (int n2 = 0; n2 < 2; ++n2) {
-        const float va = v0[n2 * 8], vb = v0[KS + n2 * 8];
-        const float vah = tf32_rn(va), vbh = tf32_rn(vb);
-        if (pv3x) {   // short sequences only: beyond 64 keys the operand rounding averages out (measured 1e-4)
+        for (int n2 = 0; n2 < 2; ++n2) {
+          const float va = v0[n2 * 8], vb = v0[KS + n2 * 8];
+          const float vah = tf32_rn(va), vbh = tf32_rn(vb);
           mma_tf32(o[n2], l0, l1, l2, l3, fbits(vah), fbits(vbh));
           mma_tf32(o[n2], a0, a1, a2, a3, fbits(va - vah), fbits(vb - vbh));
+          mma_tf32(o[n2], a0, a1, a2, a3, fbits(vah), fbits(vbh));
         }
-        mma_tf32(o[n2], a0, a1, a2, a3, fbits(vah), fbits(vbh));
+      } else {
+        const uint32_t a0 = tfbits(p0), a1 = tfbits(p2), a2 = tfbits(p1), a3 = tfbits(p3);
+        mma_tf32(o[0], a0, a1, a2, a3, tfbits(v0[0]), tfbits(v0[KS]));
+        mma_tf32(o[1], a0, a1, a2, a3, tfbits(v0[8]), tfbits(v0[KS + 8]));
       }
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
@@ -207,12 +211,49 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
   }
 }
 
-// Backward (plain TF32 with operands rounded to nearest on the fly). One CTA of 4 warps per (state, head).
-// Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved
-// log-sum-exp; D_i = sum_d dO[i][d] * O[i][d] per head.
-__device__ __forceinline__ void round_frag(uint32_t (&a)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = tfbits(__uint_as_float(a[i]));
+// Backward (plain TF32). One CTA of 4 warps per (state, head); Q (pre-scaled), K, V, dO of the head are staged once
+// in shared memory, rounded to TF32 and with the 16 columns stored in the order 0,4,1,5,2,6,3,7 | 8,12,9,13,... so
+// that the two k-steps of a score-type B fragment (columns t, t+4 and t+8, t+12) are two 8-byte loads.
+// Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved log-sum-exp;
+// D_i = sum_d dO[i][d] * O[i][d]. Accumulators start at the row constants (-lse, -D), so p = 2^(s + mask) and
+// dS = p * dp need no extra subtractions.
+__device__ __forceinline__ int perm16(int c) {
+  const int j = c & 7;
+  return (c & 8) + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
+}
+__device__ __forceinline__ void store_perm4(float* dst_row, int c4, float4 v, float scale) {
+  // columns 4*c4 .. 4*c4+3 -> positions perm16(.)
+  const int base = (c4 & 2) * 4 + (c4 & 1);     // perm16(4*c4) : c4=0 -> 0, 1 -> 1, 2 -> 8, 3 -> 9
+  dst_row[base + 0] = tf32_rn(v.x * scale);
+  dst_row[base + 2] = tf32_rn(v.y * scale);
+  dst_row[base + 4] = tf32_rn(v.z * scale);
+  dst_row[base + 6] = tf32_rn(v.w * scale);
+}
+// stage Q (scaled), K, V (columns hg.. of qkv) and dO of one head: 16-byte global loads, all four in flight
+__device__ __forceinline__ void stage_qkvg(const float* __restrict__ qkv, const float* __restrict__ dO, int hg, int L,
+                                           int Lr, float* Qs, float* Ks, float* Vs, float* Gs) {
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < Lr * 4; idx += blockDim.x) {
+    const int r = idx >> 2, c4 = idx & 3;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, g = q;
+    if (r < L) {
+      const float* row = qkv + (size_t)r * 384 + hg + c4 * 4;
+      q = *reinterpret_cast<const float4*>(row);
+      k = *reinterpret_cast<const float4*>(row + 128);
+      v = *reinterpret_cast<const float4*>(row + 256);
+      g = *reinterpret_cast<const float4*>(dO + (size_t)r * 128 + hg + c4 * 4);
+    }
+    store_perm4(Qs + r * KS, c4, q, QSCALE);
+    store_perm4(Ks + r * KS, c4, k, 1.f);
+    store_perm4(Vs + r * KS, c4, v, 1.f);
+    store_perm4(Gs + r * KS, c4, g, 1.f);
+  }
+}
+// score-type fragment of rows (row_a, row_b): {a0,a2} = row_a cols (t, t+4) of k-step kk, {a1,a3} = row_b
+__device__ __forceinline__ void lds_frag(const float* sm, int row_a, int row_b, int kk, int t, uint32_t (&a)[4]) {
+  const float2 x = *reinterpret_cast<const float2*>(sm + row_a * KS + kk * 8 + 2 * t);
+  const float2 y = *reinterpret_cast<const float2*>(sm + row_b * KS + kk * 8 + 2 * t);
+  a[0] = fbits(x.x); a[2] = fbits(x.y); a[1] = fbits(y.x); a[3] = fbits(y.y);
 }
 
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
@@ -222,12 +263,15 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   extern __shared__ float sm[];
   const int ntiles = (L + 7) >> 3;
   const int Lp = ntiles * 8;
-  float* A_s = sm;                 // phase A: K   | phase B: Q
-  float* B_s = A_s + Lp * KS;      // phase A: V   | phase B: dO
-  float* Ms = B_s + Lp * KS;       // [Lp]
-  float* Ls = Ms + Lp;             // [Lp] log-sum-exp of this head
-  float* Ds = Ls + Lp;             // [Lp]
-  int* live = reinterpret_cast<int*>(Ds + Lp);   // [ntiles]
+  const int Lr = (Lp + 15) & ~15;    // rows staged (A fragments read 16-row blocks)
+  float* Qs = sm;                    // rn(Q * QSCALE)
+  float* Ks = Qs + Lr * KS;
+  float* Vs = Ks + Lr * KS;
+  float* Gs = Vs + Lr * KS;          // dO
+  float* Ms = Gs + Lr * KS;          // [Lr] additive key mask
+  float* Ls = Ms + Lr;               // [Lr] log-sum-exp (log2 units), +inf on padding
+  float* Ds = Ls + Lr;               // [Lr]
+  int* live = reinterpret_cast<int*>(Ds + Lr);   // [ntiles]
   const int c = blockIdx.x, h = blockIdx.y;
   const float* base = qkv + (size_t)c * L * 384;
   const float* obase = att + (size_t)c * L * 128;
@@ -235,14 +279,12 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   float* dbase = dqkv + (size_t)c * L * 384;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int hg = h * 16;
-  constexpr int hc = 0;
 
-  stage_rows(base, 384, 128 + hg, L, Lp, A_s);
-  stage_rows(base, 384, 256 + hg, L, Lp, B_s);
-  for (int j = threadIdx.x; j < Lp; j += blockDim.x)
+  stage_qkvg(base, dobase, hg, L, Lr, Qs, Ks, Vs, Gs);
+  for (int j = threadIdx.x; j < Lr; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
-  for (int i = threadIdx.x; i < Lp; i += blockDim.x) {
-    float d = 0.f, l = INFINITY;   // padded queries: exp2(score - inf) == 0
+  for (int i = threadIdx.x; i < Lr; i += blockDim.x) {
+    float d = 0.f, l = INFINITY;   // padded queries: 2^(score - inf) == 0
     if (i < L) {
       const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hg);
       const float4* dp = reinterpret_cast<const float4*>(dobase + (size_t)i * 128 + hg);
@@ -251,7 +293,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
         const float4 a = op[q], b = dp[q];
         d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
       }
-      l = lse[((size_t)c * L + i) * 8 + h] * LOG2E;   // log2 units, like the recomputed scores
+      l = lse[((size_t)c * L + i) * 8 + h] * LOG2E;
     }
     Ds[i] = d;
     Ls[i] = l;
@@ -261,37 +303,38 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   __syncthreads();
   LiveBits lbits;
   lbits.load(live, ntiles);
+  const int pg = perm16(g);          // column g (and g + 8 at pg + 8) of a value-type B fragment
 
-  // ---------------- phase A: dQ ----------------
+  // ---------------- phase A: dQ = dS K / 4 ----------------
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
     uint32_t qa[2][4], da[2][4];
-    load_a_frag(base, 384, r0, L, hg, g, t, QSCALE, qa[0]);
-    load_a_frag(base, 384, r0, L, hg + 8, g, t, QSCALE, qa[1]);
-    load_a_frag(dobase, 128, r0, L, hg, g, t, 1.f, da[0]);
-    load_a_frag(dobase, 128, r0, L, hg + 8, g, t, 1.f, da[1]);
-    round_frag(qa[0]); round_frag(qa[1]); round_frag(da[0]); round_frag(da[1]);
-    const int ia = min(r0 + g, Lp - 1), ib = min(r0 + g + 8, Lp - 1);
-    const float la = Ls[ia], lb = Ls[ib];
-    const float Da = Ds[ia], Db = Ds[ib];
+    lds_frag(Qs, r0 + g, r0 + g + 8, 0, t, qa[0]);
+    lds_frag(Qs, r0 + g, r0 + g + 8, 1, t, qa[1]);
+    lds_frag(Gs, r0 + g, r0 + g + 8, 0, t, da[0]);
+    lds_frag(Gs, r0 + g, r0 + g + 8, 1, t, da[1]);
+    const float la = Ls[r0 + g], lb = Ls[r0 + g + 8];
+    const float Da = Ds[r0 + g], Db = Ds[r0 + g + 8];
     float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int nt = 0; nt < ntiles; ++nt) {
       if (!lbits.test(nt)) continue;     // masked keys: P == 0 exactly, no contribution to dQ
-      // accumulators start at the row constants: s = score - lse (log2 units), dp = dO.V^T - D
       float s[4] = {-la, -la, -lb, -lb}, dp[4] = {-Da, -Da, -Db, -Db};
-      const float* kr = A_s + (nt * 8 + g) * KS + hc + t;
-      const float* vr = B_s + (nt * 8 + g) * KS + hc + t;
-      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], tfbits(kr[0]), tfbits(kr[4]));
-      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], tfbits(kr[8]), tfbits(kr[12]));
-      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], tfbits(vr[0]), tfbits(vr[4]));
-      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], tfbits(vr[8]), tfbits(vr[12]));
-      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + mb);
-      const float p2 = ex2(s[2] + ma), p3 = ex2(s[3] + mb);
-      const uint32_t a0 = tfbits(p0 * dp[0]), a2 = tfbits(p1 * dp[1]);
-      const uint32_t a1 = tfbits(p2 * dp[2]), a3 = tfbits(p3 * dp[3]);
-      const float* k0 = A_s + (nt * 8 + 2 * t) * KS + hc + g;
-      mma_tf32(dq[0], a0, a1, a2, a3, tfbits(k0[0]), tfbits(k0[KS]));
-      mma_tf32(dq[1], a0, a1, a2, a3, tfbits(k0[8]), tfbits(k0[KS + 8]));
+      const float* kr = Ks + (nt * 8 + g) * KS + 2 * t;
+      const float* vr = Vs + (nt * 8 + g) * KS + 2 * t;
+      const float2 k01 = *reinterpret_cast<const float2*>(kr), k23 = *reinterpret_cast<const float2*>(kr + 8);
+      const float2 v01 = *reinterpret_cast<const float2*>(vr), v23 = *reinterpret_cast<const float2*>(vr + 8);
+      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(k01.x), fbits(k01.y));
+      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(k23.x), fbits(k23.y));
+      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], fbits(v01.x), fbits(v01.y));
+      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], fbits(v23.x), fbits(v23.y));
+      const float2 mk = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
+      const float p0 = ex2(s[0] + mk.x), p1 = ex2(s[1] + mk.y);
+      const float p2 = ex2(s[2] + mk.x), p3 = ex2(s[3] + mk.y);
+      // dS as A operand (k relabelled: t <-> key 2t, t+4 <-> key 2t+1); the MMA truncates it to TF32
+      const uint32_t a0 = fbits(p0 * dp[0]), a2 = fbits(p1 * dp[1]);
+      const uint32_t a1 = fbits(p2 * dp[2]), a3 = fbits(p3 * dp[3]);
+      const float* k0 = Ks + (nt * 8 + 2 * t) * KS + pg;
+      mma_tf32(dq[0], a0, a1, a2, a3, fbits(k0[0]), fbits(k0[KS]));
+      mma_tf32(dq[1], a0, a1, a2, a3, fbits(k0[8]), fbits(k0[KS + 8]));
     }
     const int ra = r0 + g, rb = r0 + g + 8;
     if (ra < L) {
@@ -305,59 +348,56 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
       *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[1][2] * 0.25f), tf32_rn(dq[1][3] * 0.25f));
     }
   }
-  __syncthreads();
 
-  // ---------------- phase B: dK, dV (rows of the tiles are KEYS, columns are QUERIES) ----------------
-  stage_rows(base, 384, hg, L, Lp, A_s);       // Q
-  stage_rows(dobase, 128, hg, L, Lp, B_s);     // dO
-  __syncthreads();
+  // ---------------- phase B: dK = dS^T Q / 4, dV = P^T dO (tile rows are KEYS, columns are QUERIES) ----------------
   for (int j0 = warp * 16; j0 < L; j0 += 64) {
     uint32_t ka[2][4], va[2][4];
-    load_a_frag(base + 128, 384, j0, L, hg, g, t, QSCALE, ka[0]);
-    load_a_frag(base + 128, 384, j0, L, hg + 8, g, t, QSCALE, ka[1]);
-    load_a_frag(base + 256, 384, j0, L, hg, g, t, 1.f, va[0]);
-    load_a_frag(base + 256, 384, j0, L, hg + 8, g, t, 1.f, va[1]);
-    round_frag(ka[0]); round_frag(ka[1]); round_frag(va[0]); round_frag(va[1]);
+    lds_frag(Ks, j0 + g, j0 + g + 8, 0, t, ka[0]);
+    lds_frag(Ks, j0 + g, j0 + g + 8, 1, t, ka[1]);
+    lds_frag(Vs, j0 + g, j0 + g + 8, 0, t, va[0]);
+    lds_frag(Vs, j0 + g, j0 + g + 8, 1, t, va[1]);
     const int ja = j0 + g, jb = j0 + g + 8;
-    const float ma = ja < L ? Ms[ja] : -INFINITY, mb = jb < L ? Ms[jb] : -INFINITY;
+    const float ma = Ms[ja], mb = Ms[jb];
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     // both 8-key tiles of this block masked: dK = dV = 0 (still written below)
     const bool dead = !lbits.test(j0 >> 3) && !(((j0 >> 3) + 1 < ntiles) && lbits.test((j0 >> 3) + 1));
     for (int it = 0; it < (dead ? 0 : ntiles); ++it) {
-      const int i0 = it * 8 + 2 * t, i1 = i0 + 1;   // query columns of this thread
-      const float l0 = Ls[i0], l1 = Ls[i1];
-      const float D0 = Ds[i0], D1 = Ds[i1];
-      float s[4] = {-l0, -l1, -l0, -l1}, dp[4] = {-D0, -D1, -D0, -D1};
-      const float* qr = A_s + (it * 8 + g) * KS + hc + t;
-      const float* dr = B_s + (it * 8 + g) * KS + hc + t;
-      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], tfbits(qr[0]), tfbits(qr[4]));
-      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], tfbits(qr[8]), tfbits(qr[12]));
-      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], tfbits(dr[0]), tfbits(dr[4]));
-      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], tfbits(dr[8]), tfbits(dr[12]));
+      const float2 l01 = *reinterpret_cast<const float2*>(Ls + it * 8 + 2 * t);   // query columns 2t, 2t+1
+      const float2 D01 = *reinterpret_cast<const float2*>(Ds + it * 8 + 2 * t);
+      float s[4] = {-l01.x, -l01.y, -l01.x, -l01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
+      const float* qr = Qs + (it * 8 + g) * KS + 2 * t;
+      const float* dr = Gs + (it * 8 + g) * KS + 2 * t;
+      const float2 q01 = *reinterpret_cast<const float2*>(qr), q23 = *reinterpret_cast<const float2*>(qr + 8);
+      const float2 d01 = *reinterpret_cast<const float2*>(dr), d23 = *reinterpret_cast<const float2*>(dr + 8);
+      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], fbits(q01.x), fbits(q01.y));
+      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], fbits(q23.x), fbits(q23.y));
+      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], fbits(d01.x), fbits(d01.y));
+      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], fbits(d23.x), fbits(d23.y));
       const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + ma);
       const float p2 = ex2(s[2] + mb), p3 = ex2(s[3] + mb);
-      const uint32_t pa0 = tfbits(p0), pa2 = tfbits(p1), pa1 = tfbits(p2), pa3 = tfbits(p3);
-      const uint32_t sa0 = tfbits(p0 * dp[0]), sa2 = tfbits(p1 * dp[1]);
-      const uint32_t sa1 = tfbits(p2 * dp[2]), sa3 = tfbits(p3 * dp[3]);
-      const float* d0 = B_s + (it * 8 + 2 * t) * KS + hc + g;
-      const float* q0 = A_s + (it * 8 + 2 * t) * KS + hc + g;
-      mma_tf32(dv[0], pa0, pa1, pa2, pa3, tfbits(d0[0]), tfbits(d0[KS]));
-      mma_tf32(dv[1], pa0, pa1, pa2, pa3, tfbits(d0[8]), tfbits(d0[KS + 8]));
-      mma_tf32(dk[0], sa0, sa1, sa2, sa3, tfbits(q0[0]), tfbits(q0[KS]));
-      mma_tf32(dk[1], sa0, sa1, sa2, sa3, tfbits(q0[8]), tfbits(q0[KS + 8]));
+      const uint32_t pa0 = fbits(p0), pa2 = fbits(p1), pa1 = fbits(p2), pa3 = fbits(p3);
+      const uint32_t sa0 = fbits(p0 * dp[0]), sa2 = fbits(p1 * dp[1]);
+      const uint32_t sa1 = fbits(p2 * dp[2]), sa3 = fbits(p3 * dp[3]);
+      const float* d0 = Gs + (it * 8 + 2 * t) * KS + pg;
+      const float* q0 = Qs + (it * 8 + 2 * t) * KS + pg;
+      mma_tf32(dv[0], pa0, pa1, pa2, pa3, fbits(d0[0]), fbits(d0[KS]));
+      mma_tf32(dv[1], pa0, pa1, pa2, pa3, fbits(d0[8]), fbits(d0[KS + 8]));
+      mma_tf32(dk[0], sa0, sa1, sa2, sa3, fbits(q0[0]), fbits(q0[KS]));
+      mma_tf32(dk[1], sa0, sa1, sa2, sa3, fbits(q0[8]), fbits(q0[KS + 8]));
     }
+    // Qs holds Q * QSCALE: dK = dS^T Q / 4 = dS^T Qs * (0.25 / QSCALE) = dS^T Qs * ln 2
     if (ja < L) {
       float* dst = dbase + (size_t)ja * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * 0.25f), tf32_rn(dk[0][1] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * 0.25f), tf32_rn(dk[1][1] * 0.25f));
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * LN2), tf32_rn(dk[0][1] * LN2));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * LN2), tf32_rn(dk[1][1] * LN2));
       *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][0]), tf32_rn(dv[0][1]));
       *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][0]), tf32_rn(dv[1][1]));
     }
     if (jb < L) {
       float* dst = dbase + (size_t)jb * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * 0.25f), tf32_rn(dk[0][3] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * 0.25f), tf32_rn(dk[1][3] * 0.25f));
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * LN2), tf32_rn(dk[0][3] * LN2));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * LN2), tf32_rn(dk[1][3] * LN2));
       *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][2]), tf32_rn(dv[0][3]));
       *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][2]), tf32_rn(dv[1][3]));
     }
@@ -387,7 +427,8 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 1024) return TPC_ERR_SHAPE;
   const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(2 * Lp * KS + 3 * Lp + Lp / 8 + 8) * sizeof(float);
+  const int Lr = (Lp + 15) & ~15;
+  const size_t smem = (size_t)(4 * Lr * KS + 3 * Lr + Lp / 8 + 8) * sizeof(float);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -46,11 +46,13 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 // Round-to-nearest (ties away) fp32 -> tf32, returned as an fp32 bit pattern. Activations and
 // weights that feed a tensor-core operand are stored already rounded so that the hardware's
 // operand truncation is exact (unbiased TF32 instead of truncation-biased TF32).
+// cvt.rna.tf32.f32 is a 4-instruction sequence on sm_100a (constant, FSETP, predicated IMAD, LOP3); for finite
+// inputs the same result is one integer add (half a TF32 ulp) and one mask.
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// operand bits for a tensor-core instruction that truncates to TF32 anyway: the add alone rounds to nearest
+__device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return __float_as_uint(x) + 0x1000u; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -1,6 +1,7 @@
 // C-ABI entry points for the stand-alone operators (unit-test granularity): tensor-core GEMMs.
 // Declared in include/tpc.h.
 #include "handle.cuh"
+#include "kernels.cuh"
 
 using namespace tpc;
 
@@ -74,6 +75,21 @@ int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, 
     d.bias[j] = db ? db + j * 128 : nullptr;
   }
   return launch_wgrad(h->tmaps, X, ldx, dY, ldy, M, Kin, Nout, d, h->num_sms, (cudaStream_t)stream);
+}
+
+// Self-attention of one encoder stack on packed qkv[C*L][384] (q | k | v); mask[c*mS + m0 + j] != 0 hides key j.
+// att[C*L][128], lse[C*L][8]. Replaces MultiHeadAttention.call's scaled_dot_product_attention + head merge
+// (agents/models/transformer/common/attention.py:37-48, common/utils.py:13-47).
+int tpc_attention_fwd(tpc_handle* h, const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att,
+                      float* lse, void* stream) {
+  if (!h || !qkv || !mask || !att) return TPC_ERR_ARG;
+  return attention_fwd(qkv, mask, mS, m0, C, L, att, lse, (cudaStream_t)stream);
+}
+// dqkv[C*L][384] from datt[C*L][128] (backward of the same ops, agents/trainer.py:115-141)
+int tpc_attention_bwd(tpc_handle* h, const float* qkv, const float* att, const float* lse, const float* datt,
+                      const float* mask, int mS, int m0, int C, int L, float* dqkv, void* stream) {
+  if (!h || !qkv || !att || !lse || !datt || !mask || !dqkv) return TPC_ERR_ARG;
+  return attention_bwd(qkv, att, lse, datt, mask, mS, m0, C, L, dqkv, (cudaStream_t)stream);
 }
 
 }  // extern "C"
