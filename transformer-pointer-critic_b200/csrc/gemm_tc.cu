@@ -385,8 +385,8 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* lofull = empty + C::ASTAGES;        // [ASTAGES]
   uint64_t* tfull = lofull + C::ASTAGES;        // [2]
   uint64_t* tempty = tfull + 2;                 // [2]
-  uint64_t* auxfull = tempty + 2;               // [1]
-  uint64_t* bfull = auxfull + 1;                // [1] weights resident
+  uint64_t* auxfull = tempty + 2;               // [4] one per staging box (aux chunk landed)
+  uint64_t* bfull = auxfull + 4;                // [1] weights resident
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -408,7 +408,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 4);
     }
-    mbar_init(auxfull, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&auxfull[a], 1);
     mbar_init(bfull, 1);
     mbar_fence_init();
   }
@@ -505,13 +505,6 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 128;
     const int q = warp & 3;
     const bool leader = (et == 0);
-    uint32_t aux_phase = 0;
-    constexpr int NPASS = 128 / C::EPI_COLS;          // 1 (full staging tile) or 2 (half)
-    constexpr int BOXES = C::EPI_COLS / BK;           // TMA boxes per pass
-    if (!SPLIT && g.aux_mode && leader && m0 < m_tiles) {
-      mbar_expect_tx(auxfull, EPI_BYTES);
-      for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, m0 * BM);
-    }
     int it = 0;
     if (g.aux_mode == 0) {
       // Streaming epilogue: every 32-column chunk goes through its own 16 KB staging box and is stored by TMA
@@ -557,62 +550,60 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (leader) tma_store_wait_all0();
-    } else {
+    } else if (!SPLIT) {
+      // Streaming epilogue with a second input (residual add / ReLU gate): the aux chunk of a 32-column box is
+      // prefetched by TMA three chunks ahead into the ring of 4 boxes, combined in place and stored right away.
+      const int my_tiles = (m_tiles - m0 + groups - 1) / groups;
+      const int nchunks = my_tiles * 4;
+      auto issue_aux = [&](int ci) {
+        const int m_t = m0 + (ci >> 2) * groups, c = ci & 3, b = ci & 3;
+        mbar_expect_tx(&auxfull[b], TILE_BYTES);
+        tma_load_2d(epi + b * TILE_BYTES, &tmAux, &auxfull[b], n_t * BN + c * BK, m_t * BM);
+      };
+      if (leader)
+        for (int ci = 0; ci < 3 && ci < nchunks; ++ci) issue_aux(ci);
+      int cidx = 0;
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        if (!SPLIT && g.aux_mode) {
-          mbar_wait(auxfull, aux_phase);
-          aux_phase ^= 1;
-        }
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-  #pragma unroll 1
-        for (int pass = 0; pass < NPASS; ++pass) {
-  #pragma unroll 1
-          for (int cc = 0; cc < BOXES; ++cc) {
-            const int c = pass * BOXES + cc;          // 32-column chunk of the accumulator
-            float v[32];
-            tmem_ld_32x32(taddr + c * 32, v);
-  #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const int c4g = c * 8 + j4;               // global float4 column of the tile
-              const int c4s = cc * 8 + j4;              // float4 column inside the staging tile
-              float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-              if (g.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c4g);
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (!SPLIT && g.aux_mode) {
-                const float4 a = *reinterpret_cast<const float4*>(epi + epi_off(et, c4s));
-                if (g.aux_mode == 1) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-                else { o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f; }
-              }
-              if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
-              *reinterpret_cast<float4*>(epi + epi_off(et, c4s)) = o;
-            }
-          }
-          if (pass == NPASS - 1) {                      // accumulator fully drained
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c, ++cidx) {
+          uint8_t* box = epi + c * TILE_BYTES;                 // box index == cidx & 3 == c
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          if (c == 3) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          mbar_wait(&auxfull[c], it & 1);                       // box c is filled once per tile
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4* slot = reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4));
+            const float4 a = *slot;
+            float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            if (g.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c * 8 + j4);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (g.aux_mode == 1) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+            else { o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f; }
+            if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+            *slot = o;
+          }
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (leader) {
-            for (int j = 0; j < BOXES; ++j)
-              tma_store_2d(&tmD, epi + j * TILE_BYTES, n_t * BN + (pass * BOXES + j) * BK, m_t * BM);
+            tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
             tma_store_commit();
-            tma_store_wait_read0();
-            const int next = m_t + groups;
-            if (!SPLIT && g.aux_mode && next < m_tiles) {
-              mbar_expect_tx(auxfull, EPI_BYTES);
-              for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, next * BM);
-            }
+            // the box of chunk cidx+3 (== box of chunk cidx-1) is free once store(cidx-1) has read it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (cidx + 3 < nchunks) issue_aux(cidx + 3);
           }
-          named_bar_sync(1, 128);
         }
       }
       if (leader) tma_store_wait_all0();
