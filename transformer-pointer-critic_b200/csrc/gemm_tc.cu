@@ -82,7 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* auxfull = tempty + 2;        // [1]
   uint64_t* lofull = auxfull + 1;        // [STAGES] A_lo of the stage is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lofull + STAGES);
+  uint64_t* auxbox = lofull + STAGES;    // [4] streaming epilogue: aux chunk of a staging box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbox + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,6 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty[a], 4);
     }
     mbar_init(auxfull, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&auxbox[a], 1);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -217,13 +219,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const bool leader = (et == 0);
     uint32_t aux_phase = 0;
+    int it = 0;
+    if (!g.ln && !g.atomic) {
+      // Streaming epilogue (bias / ReLU / aux add / aux gate / rounding): each 32-column chunk has its own 16 KB
+      // staging box; its aux chunk is prefetched by TMA three chunks ahead, the result is stored right away.
+      const int my_items = first < g.num_items ? (g.num_items - first + step - 1) / step : 0;
+      const int nchunks = my_items * 4;
+      auto issue_aux = [&](int ci) {
+        const int item = first + (ci >> 2) * step;
+        const int n_t = item % g.n_tiles, m_t = (item / g.n_tiles) / g.k_splits, c = ci & 3;
+        mbar_expect_tx(&auxbox[c], TILE_BYTES);
+        tma_load_2d(epi + c * TILE_BYTES, &tmAux, &auxbox[c], n_t * BN + c * BK, m_t * BM);
+      };
+      if (g.aux_mode && leader)
+        for (int ci = 0; ci < 3 && ci < nchunks; ++ci) issue_aux(ci);
+      int cidx = 0;
+      for (int item = first; item < g.num_items; item += step, ++it) {
+        const int n_t = item % g.n_tiles;
+        const int m_t = (item / g.n_tiles) / g.k_splits;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c, ++cidx) {
+          uint8_t* box = epi + c * TILE_BYTES;
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          if (c == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (g.aux_mode) mbar_wait(&auxbox[c], it & 1);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4* slot = reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4));
+            float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            if (g.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n_t * BN) + c * 8 + j4);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (g.aux_mode) {
+              const float4 a = *slot;
+              if (g.aux_mode == 1) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+              else { o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f; }
+            }
+            if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+            *slot = o;
+          }
+          // without aux the box about to be rewritten three chunks later only needs its old store to be done
+          if (!g.aux_mode && leader) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
+            tma_store_commit();
+            if (g.aux_mode) {
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              if (cidx + 3 < nchunks) issue_aux(cidx + 3);
+            }
+          }
+        }
+      }
+      if (leader) tma_store_wait_all0();
+    } else {
     if (g.aux_mode && leader && first < g.num_items) {
       const int n_t = first % g.n_tiles;
       const int m_t = (first / g.n_tiles) / g.k_splits;
       mbar_expect_tx(auxfull, EPI_BYTES);
       for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, m_t * BM);
     }
-    int it = 0;
     for (int item = first; item < g.num_items; item += step, ++it) {
       const int n_t = item % g.n_tiles;
       const int m_t = (item / g.n_tiles) / g.k_splits;
@@ -342,6 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar_sync(1, 128);
     }
     if (leader) tma_store_wait_all0();
+    }
   }
 
   tc_fence_before();
