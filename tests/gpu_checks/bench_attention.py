@@ -45,7 +45,8 @@ def run(Cn, Lt, frac_masked, check):
         us = e0.elapsed_time(e1) / 5 * 1e3
         print(f"attention {name} C={Cn} L={Lt} masked={frac_masked}: {us:8.1f} us  ({us / Cn * 148:.2f} us per state-SM)")
 
-for (Cn, Lt, fm) in [(5, 151, 0.3), (7, 100, 0.5), (9, 51, 0.0), (3, 16, 0.25)]:
-    run(Cn, Lt, fm, True)
+if not os.environ.get('SKIP_CHECK'):
+    for (Cn, Lt, fm) in [(5, 151, 0.3), (7, 100, 0.5), (9, 51, 0.0), (3, 16, 0.25)]:
+        run(Cn, Lt, fm, True)
 for (Lt, fm) in [(151, 0.0), (151, 0.33), (100, 0.5), (51, 0.1)]:
     run(2048, Lt, fm, False)

@@ -34,14 +34,25 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float QSCALE = 0.25f * LOG2E;   // 1/sqrt(depth=16), scores kept in log2 units so that exp == one ex2
 __device__ __forceinline__ uint32_t tfbits(float x) { return tf32_rn_bits(x); }   // MMA truncates: add == round
 
-// stage the 16 columns of one head (at column offset col0 of a [rows][ld] matrix) of L rows into smem [Lp][KS]
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int ld, int col0, int L, int Lp, float* dst) {
-  for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
+// Asynchronous staging (cp.async, 16 B, L1 bypass) of the 16 columns of one head of rows [0, Lr) into smem [Lr][KS];
+// rows >= L are zero-filled. All copies of a CTA are in flight together (one commit group): the kernels are bound
+// by this staging latency, not by the tile math (measured: removing the inner loops changes the time by < 30 %).
+__device__ __forceinline__ void stage_async(const float* __restrict__ src, int ld, int col0, int L, int Lr, float* dst) {
+  for (int idx = threadIdx.x; idx < Lr * 4; idx += blockDim.x) {
     const int r = idx >> 2, c4 = idx & 3;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < L) v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + col0 + c4 * 4);
-    *reinterpret_cast<float4*>(dst + r * KS + c4 * 4) = v;
+    const float* g = src + (size_t)min(r, L - 1) * ld + col0 + c4 * 4;
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * KS + c4 * 4));
+    const int bytes = r < L ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
   }
+}
+// A fragment (rows row_a / row_b, columns c0 + t and c0 + t + 4) from a staged smem tile, scaled, TF32-rounded bits
+__device__ __forceinline__ void lds_a_frag(const float* sm, int row_a, int row_b, int c0, int t, float scale,
+                                           uint32_t (&a)[4]) {
+  a[0] = tf32_rn_bits(sm[row_a * KS + c0 + t] * scale);
+  a[1] = tf32_rn_bits(sm[row_b * KS + c0 + t] * scale);
+  a[2] = tf32_rn_bits(sm[row_a * KS + c0 + t + 4] * scale);
+  a[3] = tf32_rn_bits(sm[row_b * KS + c0 + t + 4] * scale);
 }
 
 // A fragment (16 rows x 8 cols at column c0) of a global row-major matrix; rows clamped to L-1
@@ -114,21 +125,25 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
   float* Ms = Vs + Lp * KS;  // additive key mask: mask * -1e9, -inf beyond L
   int* live = reinterpret_cast<int*>(Ms + Lp);   // [ntiles] 1 if the 8-key tile holds an unmasked key
   int* lidx = live + ntiles;                     // [ntiles] compact list of live tiles
-  const int c = blockIdx.x, h = blockIdx.y;
+  // heads are the fastest-varying block index: the 8 CTAs of a state run side by side and share the 128-byte
+  // lines / DRAM pages of its rows (a head only touches 64 B of each 1536 B qkv row)
+  const int c = blockIdx.x >> 3, h = blockIdx.x & 7;
   const int hg = h * 16;                       // this head's column offset in global memory
   constexpr int hc = 0;                        // ... and in shared memory (only this head is staged)
   const float* base = qkv + (size_t)c * L * 384;
-  stage_rows(base, 384, 128 + hg, L, Lp, Ks);
-  stage_rows(base, 384, 256 + hg, L, Lp, Vs);
+  stage_async(base, 384, 128 + hg, L, Lp, Ks);
+  stage_async(base, 384, 256 + hg, L, Lp, Vs);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int j = threadIdx.x; j < Lp; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   __syncthreads();
-  mark_live_tiles(Ms, live, ntiles);
+  mark_live_tiles(Ms, live, ntiles);   // the mask bookkeeping runs while the K / V copies are in flight
   __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const bool pv3x = L < 64;
   const int nlive = compact_live(live, lidx, ntiles);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
     uint32_t qh[2][4], ql[2][4];
 #pragma unroll
@@ -225,51 +240,11 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
   }
 }
 
-// Backward (plain TF32). One CTA of 4 warps per (state, head); Q (pre-scaled), K, V, dO of the head are staged once
-// in shared memory, rounded to TF32 and with the 16 columns stored in the order 0,4,1,5,2,6,3,7 | 8,12,9,13,... so
-// that the two k-steps of a score-type B fragment (columns t, t+4 and t+8, t+12) are two 8-byte loads.
-// Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed from the saved log-sum-exp;
-// D_i = sum_d dO[i][d] * O[i][d]. Accumulators start at the row constants (-lse, -D), so p = 2^(s + mask) and
-// dS = p * dp need no extra subtractions.
-__device__ __forceinline__ int perm16(int c) {
-  const int j = c & 7;
-  return (c & 8) + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
-}
-__device__ __forceinline__ void store_perm4(float* dst_row, int c4, float4 v, float scale) {
-  // columns 4*c4 .. 4*c4+3 -> positions perm16(.)
-  const int base = (c4 & 2) * 4 + (c4 & 1);     // perm16(4*c4) : c4=0 -> 0, 1 -> 1, 2 -> 8, 3 -> 9
-  dst_row[base + 0] = tf32_rn(v.x * scale);
-  dst_row[base + 2] = tf32_rn(v.y * scale);
-  dst_row[base + 4] = tf32_rn(v.z * scale);
-  dst_row[base + 6] = tf32_rn(v.w * scale);
-}
-// stage Q (scaled), K, V (columns hg.. of qkv) and dO of one head: 16-byte global loads, all four in flight
-__device__ __forceinline__ void stage_qkvg(const float* __restrict__ qkv, const float* __restrict__ dO, int hg, int L,
-                                           int Lr, float* Qs, float* Ks, float* Vs, float* Gs) {
-#pragma unroll 2
-  for (int idx = threadIdx.x; idx < Lr * 4; idx += blockDim.x) {
-    const int r = idx >> 2, c4 = idx & 3;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, g = q;
-    if (r < L) {
-      const float* row = qkv + (size_t)r * 384 + hg + c4 * 4;
-      q = *reinterpret_cast<const float4*>(row);
-      k = *reinterpret_cast<const float4*>(row + 128);
-      v = *reinterpret_cast<const float4*>(row + 256);
-      g = *reinterpret_cast<const float4*>(dO + (size_t)r * 128 + hg + c4 * 4);
-    }
-    store_perm4(Qs + r * KS, c4, q, QSCALE);
-    store_perm4(Ks + r * KS, c4, k, 1.f);
-    store_perm4(Vs + r * KS, c4, v, 1.f);
-    store_perm4(Gs + r * KS, c4, g, 1.f);
-  }
-}
-// score-type fragment of rows (row_a, row_b): {a0,a2} = row_a cols (t, t+4) of k-step kk, {a1,a3} = row_b
-__device__ __forceinline__ void lds_frag(const float* sm, int row_a, int row_b, int kk, int t, uint32_t (&a)[4]) {
-  const float2 x = *reinterpret_cast<const float2*>(sm + row_a * KS + kk * 8 + 2 * t);
-  const float2 y = *reinterpret_cast<const float2*>(sm + row_b * KS + kk * 8 + 2 * t);
-  a[0] = fbits(x.x); a[2] = fbits(x.y); a[1] = fbits(y.x); a[3] = fbits(y.y);
-}
-
+// Backward (plain TF32). One CTA of 4 warps per (state, head); Q, K, V, dO of the head are staged once in shared
+// memory with cp.async (all copies in flight together) while D_i = sum_d dO[i][d] * O[i][d] and the log-sum-exp are
+// gathered from global memory. Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed
+// from the saved log-sum-exp. Accumulators start at the row constants (-lse, -D), so p = 2^(s + mask) and
+// dS = p * dp need no extra subtractions. Operands are rounded to TF32 with one integer add at fragment load.
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
                                                        const float* __restrict__ lse, const float* __restrict__ datt,
                                                        const float* __restrict__ mask, int mS, int m0, int L,
@@ -278,7 +253,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   const int ntiles = (L + 7) >> 3;
   const int Lp = ntiles * 8;
   const int Lr = (Lp + 15) & ~15;    // rows staged (A fragments read 16-row blocks)
-  float* Qs = sm;                    // rn(Q * QSCALE)
+  float* Qs = sm;
   float* Ks = Qs + Lr * KS;
   float* Vs = Ks + Lr * KS;
   float* Gs = Vs + Lr * KS;          // dO
@@ -287,7 +262,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   float* Ds = Ls + Lr;               // [Lr]
   int* live = reinterpret_cast<int*>(Ds + Lr);   // [ntiles]
   int* lidx = live + ntiles;                     // [ntiles] compact list of live tiles
-  const int c = blockIdx.x, h = blockIdx.y;
+  // heads are the fastest-varying block index: the 8 CTAs of a state run side by side and share the 128-byte
+  // lines / DRAM pages of its rows (a head only touches 64 B of each 1536 B qkv row)
+  const int c = blockIdx.x >> 3, h = blockIdx.x & 7;
   const float* base = qkv + (size_t)c * L * 384;
   const float* obase = att + (size_t)c * L * 128;
   const float* dobase = datt + (size_t)c * L * 128;
@@ -295,7 +272,11 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int hg = h * 16;
 
-  stage_qkvg(base, dobase, hg, L, Lr, Qs, Ks, Vs, Gs);
+  stage_async(base, 384, hg, L, Lr, Qs);
+  stage_async(base, 384, 128 + hg, L, Lr, Ks);
+  stage_async(base, 384, 256 + hg, L, Lr, Vs);
+  stage_async(dobase, 128, hg, L, Lr, Gs);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int j = threadIdx.x; j < Lr; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   for (int i = threadIdx.x; i < Lr; i += blockDim.x) {
@@ -303,10 +284,12 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     if (i < L) {
       const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hg);
       const float4* dp = reinterpret_cast<const float4*>(dobase + (size_t)i * 128 + hg);
+      float4 a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = op[q]; b[q] = dp[q]; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 a = op[q], b = dp[q];
-        d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
+        d = fmaf(a[q].x, b[q].x, d); d = fmaf(a[q].y, b[q].y, d); d = fmaf(a[q].z, b[q].z, d); d = fmaf(a[q].w, b[q].w, d);
       }
       l = lse[((size_t)c * L + i) * 8 + h] * LOG2E;
     }
@@ -314,20 +297,21 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     Ls[i] = l;
   }
   __syncthreads();
-  mark_live_tiles(Ms, live, ntiles);
+  mark_live_tiles(Ms, live, ntiles);   // the mask bookkeeping runs while the copies are in flight
   __syncthreads();
   LiveBits lbits;
   lbits.load(live, ntiles);
   const int nlive = compact_live(live, lidx, ntiles);
-  const int pg = perm16(g);          // column g (and g + 8 at pg + 8) of a value-type B fragment
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
 
   // ---------------- phase A: dQ = dS K / 4 ----------------
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
     uint32_t qa[2][4], da[2][4];
-    lds_frag(Qs, r0 + g, r0 + g + 8, 0, t, qa[0]);
-    lds_frag(Qs, r0 + g, r0 + g + 8, 1, t, qa[1]);
-    lds_frag(Gs, r0 + g, r0 + g + 8, 0, t, da[0]);
-    lds_frag(Gs, r0 + g, r0 + g + 8, 1, t, da[1]);
+    lds_a_frag(Qs, r0 + g, r0 + g + 8, 0, t, QSCALE, qa[0]);
+    lds_a_frag(Qs, r0 + g, r0 + g + 8, 8, t, QSCALE, qa[1]);
+    lds_a_frag(Gs, r0 + g, r0 + g + 8, 0, t, 1.f, da[0]);
+    lds_a_frag(Gs, r0 + g, r0 + g + 8, 8, t, 1.f, da[1]);
     const float la = Ls[r0 + g], lb = Ls[r0 + g + 8];
     const float Da = Ds[r0 + g], Db = Ds[r0 + g + 8];
     float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -335,23 +319,21 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     for (int li = 0; li < nlive; ++li) {   // live key tiles only (masked keys: P == 0 exactly)
       const int nt = lidx[li];
       float s[4] = {-la, -la, -lb, -lb}, dp[4] = {-Da, -Da, -Db, -Db};
-      const float* kr = Ks + (nt * 8 + g) * KS + 2 * t;
-      const float* vr = Vs + (nt * 8 + g) * KS + 2 * t;
-      const float2 k01 = *reinterpret_cast<const float2*>(kr), k23 = *reinterpret_cast<const float2*>(kr + 8);
-      const float2 v01 = *reinterpret_cast<const float2*>(vr), v23 = *reinterpret_cast<const float2*>(vr + 8);
-      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], fbits(k01.x), fbits(k01.y));
-      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], fbits(k23.x), fbits(k23.y));
-      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], fbits(v01.x), fbits(v01.y));
-      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], fbits(v23.x), fbits(v23.y));
+      const float* kr = Ks + (nt * 8 + g) * KS + t;
+      const float* vr = Vs + (nt * 8 + g) * KS + t;
+      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], tfbits(kr[0]), tfbits(kr[4]));
+      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], tfbits(kr[8]), tfbits(kr[12]));
+      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], tfbits(vr[0]), tfbits(vr[4]));
+      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], tfbits(vr[8]), tfbits(vr[12]));
       const float2 mk = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
       const float p0 = ex2(s[0] + mk.x), p1 = ex2(s[1] + mk.y);
       const float p2 = ex2(s[2] + mk.x), p3 = ex2(s[3] + mk.y);
-      // dS as A operand (k relabelled: t <-> key 2t, t+4 <-> key 2t+1); the MMA truncates it to TF32
-      const uint32_t a0 = fbits(p0 * dp[0]), a2 = fbits(p1 * dp[1]);
-      const uint32_t a1 = fbits(p2 * dp[2]), a3 = fbits(p3 * dp[3]);
-      const float* k0 = Ks + (nt * 8 + 2 * t) * KS + pg;
-      mma_tf32(dq[0], a0, a1, a2, a3, fbits(k0[0]), fbits(k0[KS]));
-      mma_tf32(dq[1], a0, a1, a2, a3, fbits(k0[8]), fbits(k0[KS + 8]));
+      // dS as A operand (k relabelled: t <-> key 2t, t+4 <-> key 2t+1)
+      const uint32_t a0 = tfbits(p0 * dp[0]), a2 = tfbits(p1 * dp[1]);
+      const uint32_t a1 = tfbits(p2 * dp[2]), a3 = tfbits(p3 * dp[3]);
+      const float* k0 = Ks + (nt * 8 + 2 * t) * KS + g;
+      mma_tf32(dq[0], a0, a1, a2, a3, tfbits(k0[0]), tfbits(k0[KS]));
+      mma_tf32(dq[1], a0, a1, a2, a3, tfbits(k0[8]), tfbits(k0[KS + 8]));
     }
     const int ra = r0 + g, rb = r0 + g + 8;
     if (ra < L) {
@@ -369,10 +351,10 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   // ---------------- phase B: dK = dS^T Q / 4, dV = P^T dO (tile rows are KEYS, columns are QUERIES) ----------------
   for (int j0 = warp * 16; j0 < L; j0 += 64) {
     uint32_t ka[2][4], va[2][4];
-    lds_frag(Ks, j0 + g, j0 + g + 8, 0, t, ka[0]);
-    lds_frag(Ks, j0 + g, j0 + g + 8, 1, t, ka[1]);
-    lds_frag(Vs, j0 + g, j0 + g + 8, 0, t, va[0]);
-    lds_frag(Vs, j0 + g, j0 + g + 8, 1, t, va[1]);
+    lds_a_frag(Ks, j0 + g, j0 + g + 8, 0, t, QSCALE, ka[0]);
+    lds_a_frag(Ks, j0 + g, j0 + g + 8, 8, t, QSCALE, ka[1]);
+    lds_a_frag(Vs, j0 + g, j0 + g + 8, 0, t, 1.f, va[0]);
+    lds_a_frag(Vs, j0 + g, j0 + g + 8, 8, t, 1.f, va[1]);
     const int ja = j0 + g, jb = j0 + g + 8;
     const float ma = Ms[ja], mb = Ms[jb];
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -384,38 +366,35 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
       const float2 l01 = *reinterpret_cast<const float2*>(Ls + it * 8 + 2 * t);   // query columns 2t, 2t+1
       const float2 D01 = *reinterpret_cast<const float2*>(Ds + it * 8 + 2 * t);
       float s[4] = {-l01.x, -l01.y, -l01.x, -l01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
-      const float* qr = Qs + (it * 8 + g) * KS + 2 * t;
-      const float* dr = Gs + (it * 8 + g) * KS + 2 * t;
-      const float2 q01 = *reinterpret_cast<const float2*>(qr), q23 = *reinterpret_cast<const float2*>(qr + 8);
-      const float2 d01 = *reinterpret_cast<const float2*>(dr), d23 = *reinterpret_cast<const float2*>(dr + 8);
-      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], fbits(q01.x), fbits(q01.y));
-      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], fbits(q23.x), fbits(q23.y));
-      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], fbits(d01.x), fbits(d01.y));
-      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], fbits(d23.x), fbits(d23.y));
+      const float* qr = Qs + (it * 8 + g) * KS + t;
+      const float* dr = Gs + (it * 8 + g) * KS + t;
+      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], tfbits(qr[0]), tfbits(qr[4]));
+      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], tfbits(qr[8]), tfbits(qr[12]));
+      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], tfbits(dr[0]), tfbits(dr[4]));
+      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], tfbits(dr[8]), tfbits(dr[12]));
       const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + ma);
       const float p2 = ex2(s[2] + mb), p3 = ex2(s[3] + mb);
-      const uint32_t pa0 = fbits(p0), pa2 = fbits(p1), pa1 = fbits(p2), pa3 = fbits(p3);
-      const uint32_t sa0 = fbits(p0 * dp[0]), sa2 = fbits(p1 * dp[1]);
-      const uint32_t sa1 = fbits(p2 * dp[2]), sa3 = fbits(p3 * dp[3]);
-      const float* d0 = Gs + (it * 8 + 2 * t) * KS + pg;
-      const float* q0 = Qs + (it * 8 + 2 * t) * KS + pg;
-      mma_tf32(dv[0], pa0, pa1, pa2, pa3, fbits(d0[0]), fbits(d0[KS]));
-      mma_tf32(dv[1], pa0, pa1, pa2, pa3, fbits(d0[8]), fbits(d0[KS + 8]));
-      mma_tf32(dk[0], sa0, sa1, sa2, sa3, fbits(q0[0]), fbits(q0[KS]));
-      mma_tf32(dk[1], sa0, sa1, sa2, sa3, fbits(q0[8]), fbits(q0[KS + 8]));
+      const uint32_t pa0 = tfbits(p0), pa2 = tfbits(p1), pa1 = tfbits(p2), pa3 = tfbits(p3);
+      const uint32_t sa0 = tfbits(p0 * dp[0]), sa2 = tfbits(p1 * dp[1]);
+      const uint32_t sa1 = tfbits(p2 * dp[2]), sa3 = tfbits(p3 * dp[3]);
+      const float* d0 = Gs + (it * 8 + 2 * t) * KS + g;
+      const float* q0 = Qs + (it * 8 + 2 * t) * KS + g;
+      mma_tf32(dv[0], pa0, pa1, pa2, pa3, tfbits(d0[0]), tfbits(d0[KS]));
+      mma_tf32(dv[1], pa0, pa1, pa2, pa3, tfbits(d0[8]), tfbits(d0[KS + 8]));
+      mma_tf32(dk[0], sa0, sa1, sa2, sa3, tfbits(q0[0]), tfbits(q0[KS]));
+      mma_tf32(dk[1], sa0, sa1, sa2, sa3, tfbits(q0[8]), tfbits(q0[KS + 8]));
     }
-    // Qs holds Q * QSCALE: dK = dS^T Q / 4 = dS^T Qs * (0.25 / QSCALE) = dS^T Qs * ln 2
     if (ja < L) {
       float* dst = dbase + (size_t)ja * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * LN2), tf32_rn(dk[0][1] * LN2));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * LN2), tf32_rn(dk[1][1] * LN2));
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * 0.25f), tf32_rn(dk[0][1] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * 0.25f), tf32_rn(dk[1][1] * 0.25f));
       *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][0]), tf32_rn(dv[0][1]));
       *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][0]), tf32_rn(dv[1][1]));
     }
     if (jb < L) {
       float* dst = dbase + (size_t)jb * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * LN2), tf32_rn(dk[0][3] * LN2));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * LN2), tf32_rn(dk[1][3] * LN2));
+      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * 0.25f), tf32_rn(dk[0][3] * 0.25f));
+      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * 0.25f), tf32_rn(dk[1][3] * 0.25f));
       *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][2]), tf32_rn(dv[0][3]));
       *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][2]), tf32_rn(dv[1][3]));
     }
@@ -435,7 +414,7 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
     TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  attn_fwd_kernel<<<dim3(C, 8), 128, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
+  attn_fwd_kernel<<<C * 8, 128, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
@@ -452,7 +431,7 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
     TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  attn_bwd_kernel<<<dim3(C, 8), 128, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
+  attn_bwd_kernel<<<C * 8, 128, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
