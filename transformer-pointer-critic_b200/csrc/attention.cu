@@ -12,6 +12,17 @@ namespace tpc {
 
 namespace {
 
+// phase stamps for tests/gpu_checks/micro/attn_phase.cu (compiled out of the library)
+#ifdef ATTN_PROFILE
+__device__ long long attn_prof[8 * 32768];
+#define ATTN_STAMP(i)                                                                    \
+  do {                                                                                    \
+    if (threadIdx.x == 0 && blockIdx.x < 32768) attn_prof[blockIdx.x * 8 + (i)] = clock64(); \
+  } while (0)
+#else
+#define ATTN_STAMP(i)
+#endif
+
 constexpr int KS = 20;   // smem row stride in floats (16 of one head + 4): conflict-free fragment loads
 constexpr float BIG_NUMBER = 1e9f;
 
@@ -109,135 +120,274 @@ struct LiveBits {
   __device__ __forceinline__ bool test(int nt) const { return nt >= 64 || ((w >> nt) & 1ull); }
 };
 
-// Forward: one CTA of 4 warps per (state, head) -- ~26 KB of smem at 151 tokens, so 8 CTAs share an SM and one
-// CTA's staging latency hides behind the others' math; the warps take alternating 16-row query blocks.
-// Two passes over the keys keep the register footprint small: pass 1 finds the row maximum (plain TF32),
-// pass 2 recomputes the scores in 3xTF32 (hi/lo split of Q and K: fp32-level logits, the softmax amplifies
-// score errors), exponentiates and accumulates P.V (P, V rounded to nearest TF32).
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
-                                                       int mS, int m0, int L, float* __restrict__ att,
-                                                       float* __restrict__ lse) {
+// ---- forward operand images in shared memory ----
+// Kc[key][KC]: the key's 16 values as TF32 hi (floats 0..15) and lo = k - hi (16..31), each 8-column group stored
+// as (c0, c4, c1, c5, c2, c6, c3, c7) so the B fragment pair (k = t, k = t + 4) of an m16n8k8 MMA is one LDS.64.
+// Vt[d][VS]: V transposed and rounded, so the P.V fragment pair (keys 2t, 2t + 1) is one LDS.64 as well.
+// The strides (40, VS mod 32 in {8, 24}) keep both half-warp access patterns bank-conflict free.
+constexpr int KC = 40;
+__host__ __device__ inline int vt_stride(int Lp) { return (Lp % 32 == 0 || Lp % 32 == 16) ? Lp + 8 : Lp; }
+// scores are kept in log2 units; when |q| * max|k| stays below this bound the softmax needs no row-max pass
+// (2^s can neither overflow nor lose a term to underflow, and p / sum is scale invariant in floating point)
+constexpr float EASY_BOUND = 96.f;
+
+__device__ __forceinline__ void store_k_row(float* row, const float4 (&k)[4]) {
+  const float x[16] = {k[0].x, k[0].y, k[0].z, k[0].w, k[1].x, k[1].y, k[1].z, k[1].w,
+                       k[2].x, k[2].y, k[2].z, k[2].w, k[3].x, k[3].y, k[3].z, k[3].w};
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = tf32_rn(x[i]);
+    lo[i] = x[i] - hi[i];
+  }
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    const int o = kk * 8;
+    *reinterpret_cast<float4*>(row + o) = make_float4(hi[o], hi[o + 4], hi[o + 1], hi[o + 5]);
+    *reinterpret_cast<float4*>(row + o + 4) = make_float4(hi[o + 2], hi[o + 6], hi[o + 3], hi[o + 7]);
+    *reinterpret_cast<float4*>(row + 16 + o) = make_float4(lo[o], lo[o + 4], lo[o + 1], lo[o + 5]);
+    *reinterpret_cast<float4*>(row + 16 + o + 4) = make_float4(lo[o + 2], lo[o + 6], lo[o + 3], lo[o + 7]);
+  }
+}
+
+// RB 16-row query blocks (rows r0 + 64 b) of one warp against all live key tiles. The blocks share every K / V
+// fragment load and give the scheduler RB independent MMA chains: the loop is latency bound, not issue bound.
+template <int RB, bool PV3X>
+__device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, int r0, int L, int hg, int h, int g, int t,
+                                               const float* Kc, const float* Vt, const float* Vl, int VS,
+                                               const float* Ms, const int* lidx, int nlive, float kmax2,
+                                               float* __restrict__ att_c, float* __restrict__ lse_c) {
+  uint32_t qh[RB][2][4], ql[RB][2][4];
+  float q2 = 0.f;
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+    float qa2 = 0.f, qb2 = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t raw[4];
+      load_a_frag(base, 384, r0 + 64 * b, L, hg + kk * 8, g, t, QSCALE, raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = __uint_as_float(raw[i]);
+        const float hi = tf32_rn(x);
+        qh[b][kk][i] = __float_as_uint(hi);
+        ql[b][kk][i] = __float_as_uint(x - hi);
+        if (i & 1) qb2 = fmaf(x, x, qb2); else qa2 = fmaf(x, x, qa2);
+      }
+    }
+    // |q|^2 of the block's rows (4 lanes hold a row)
+    qa2 += __shfl_xor_sync(0xffffffffu, qa2, 1);
+    qa2 += __shfl_xor_sync(0xffffffffu, qa2, 2);
+    qb2 += __shfl_xor_sync(0xffffffffu, qb2, 1);
+    qb2 += __shfl_xor_sync(0xffffffffu, qb2, 2);
+    q2 = fmaxf(q2, fmaxf(qa2, qb2));
+  }
+  q2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(q2)));   // warp uniform
+  const bool easy = q2 * kmax2 < EASY_BOUND * EASY_BOUND;   // NaN / inf take the two-pass path
+  // ---- pass 1 (rare): row maxima
+  float mx[RB][2];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) mx[b][0] = mx[b][1] = 0.f;
+  if (!easy) {
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mx[b][0] = mx[b][1] = -INFINITY;
+    for (int li = 0; li < nlive; ++li) {
+      const int nt = lidx[li];
+      const float* kr = Kc + (nt * 8 + g) * KC + 2 * t;
+      const float2 h0 = *reinterpret_cast<const float2*>(kr), h1 = *reinterpret_cast<const float2*>(kr + 8);
+      const float2 mk = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_tf32(s, qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(h0.x), fbits(h0.y));
+        mma_tf32(s, qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(h1.x), fbits(h1.y));
+        mx[b][0] = fmaxf(mx[b][0], fmaxf(s[0] + mk.x, s[1] + mk.y));
+        mx[b][1] = fmaxf(mx[b][1], fmaxf(s[2] + mk.x, s[3] + mk.y));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[b][r] = fmaxf(mx[b][r], __shfl_xor_sync(0xffffffffu, mx[b][r], 1));
+        mx[b][r] = fmaxf(mx[b][r], __shfl_xor_sync(0xffffffffu, mx[b][r], 2));
+      }
+  }
+  // ---- pass 2: exact scores, softmax numerators, P.V
+  float sum[RB][2], o[RB][2][4];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+    sum[b][0] = sum[b][1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[b][0][i] = o[b][1][i] = 0.f;
+  }
+  const float* kbase = Kc + g * KC + 2 * t;
+  const float* vbase = Vt + g * VS + 2 * t;
+  const float* mbase = Ms + 2 * t;
+#pragma unroll 2
+  for (int li = 0; li < nlive; ++li) {
+    const int nt = lidx[li];
+    const float* kr = kbase + nt * (8 * KC);
+    const float2 kh0 = *reinterpret_cast<const float2*>(kr), kh1 = *reinterpret_cast<const float2*>(kr + 8);
+    const float2 kl0 = *reinterpret_cast<const float2*>(kr + 16), kl1 = *reinterpret_cast<const float2*>(kr + 24);
+    const float2 mk = *reinterpret_cast<const float2*>(mbase + nt * 8);
+    // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
+    const float* vr = vbase + nt * 8;
+    const float2 v0 = *reinterpret_cast<const float2*>(vr), v1 = *reinterpret_cast<const float2*>(vr + 8 * VS);
+    float2 w0 = v0, w1 = v1;
+    if (PV3X) {
+      w0 = *reinterpret_cast<const float2*>(vr + (Vl - Vt));
+      w1 = *reinterpret_cast<const float2*>(vr + (Vl - Vt) + 8 * VS);
+    }
+    float sc[RB][4];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      sc[b][0] = sc[b][1] = -mx[b][0];     // accumulate score - rowmax directly
+      sc[b][2] = sc[b][3] = -mx[b][1];
+    }
+    // small terms first; the RB chains are independent and interleave
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], ql[b][0][0], ql[b][0][1], ql[b][0][2], ql[b][0][3], fbits(kh0.x), fbits(kh0.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(kl0.x), fbits(kl0.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], ql[b][1][0], ql[b][1][1], ql[b][1][2], ql[b][1][3], fbits(kh1.x), fbits(kh1.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(kl1.x), fbits(kl1.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(kh0.x), fbits(kh0.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(kh1.x), fbits(kh1.y));
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      const float p0 = ex2(sc[b][0] + mk.x), p1 = ex2(sc[b][1] + mk.y);
+      const float p2 = ex2(sc[b][2] + mk.x), p3 = ex2(sc[b][3] + mk.y);
+      sum[b][0] += p0 + p1;
+      sum[b][1] += p2 + p3;
+      if (PV3X) {
+        // short sequences: 3xTF32 again (with few keys there is no averaging of the operand rounding)
+        const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
+        const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
+        const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
+        mma_tf32(o[b][0], l0, l1, l2, l3, fbits(v0.x), fbits(v0.y));
+        mma_tf32(o[b][1], l0, l1, l2, l3, fbits(v1.x), fbits(v1.y));
+        mma_tf32(o[b][0], a0, a1, a2, a3, fbits(w0.x), fbits(w0.y));
+        mma_tf32(o[b][1], a0, a1, a2, a3, fbits(w1.x), fbits(w1.y));
+        mma_tf32(o[b][0], a0, a1, a2, a3, fbits(v0.x), fbits(v0.y));
+        mma_tf32(o[b][1], a0, a1, a2, a3, fbits(v1.x), fbits(v1.y));
+      } else {
+        const uint32_t a0 = tfbits(p0), a1 = tfbits(p2), a2 = tfbits(p1), a3 = tfbits(p3);
+        mma_tf32(o[b][0], a0, a1, a2, a3, fbits(v0.x), fbits(v0.y));
+        mma_tf32(o[b][1], a0, a1, a2, a3, fbits(v1.x), fbits(v1.y));
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float sm_ = sum[b][r];
+      sm_ += __shfl_xor_sync(0xffffffffu, sm_, 1);
+      sm_ += __shfl_xor_sync(0xffffffffu, sm_, 2);
+      const float inv = 1.f / sm_;
+      const int row = r0 + 64 * b + g + 8 * r;
+      if (row < L) {
+        float* dst = att_c + (size_t)row * 128 + hg + 2 * t;
+        *reinterpret_cast<float2*>(dst) = make_float2(o[b][0][2 * r] * inv, o[b][0][2 * r + 1] * inv);
+        *reinterpret_cast<float2*>(dst + 8) = make_float2(o[b][1][2 * r] * inv, o[b][1][2 * r + 1] * inv);
+        if (t == 0 && lse_c) lse_c[(size_t)row * 8 + h] = mx[b][r] * LN2 + logf(sm_);   // natural-log units
+      }
+    }
+  }
+}
+
+// Forward: one CTA of 4 warps per (state, head); ~35 KB of smem at 151 tokens, so 5-6 CTAs share an SM and one
+// CTA's staging latency hides behind the others' math; the warps take alternating 16-row query blocks, two at a time.
+// Scores are 3xTF32 (hi/lo split of Q and K: fp32-level logits, the softmax amplifies score errors); P.V is plain
+// TF32 with P, V rounded to nearest (3xTF32 below 64 tokens, where there is no averaging of the rounding).
+// The row maximum is only searched (pass 1) when the norm bound says the exponentials could leave fp32 range.
+template <bool PV3X>
+__global__ void __launch_bounds__(128, 5) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                          int mS, int m0, int L, float* __restrict__ att,
+                                                          float* __restrict__ lse) {
   extern __shared__ float sm[];
+  __shared__ unsigned kmax_bits;
   const int ntiles = (L + 7) >> 3;
   const int Lp = ntiles * 8;
-  float* Ks = sm;
-  float* Vs = Ks + Lp * KS;
-  float* Ms = Vs + Lp * KS;  // additive key mask: mask * -1e9, -inf beyond L
+  const int VS = vt_stride(Lp);
+  float* Kc = sm;
+  float* Vt = Kc + Lp * KC;
+  float* Vl = Vt + 16 * VS;                       // lo part of V, only when PV3X
+  float* Ms = Vl + (PV3X ? 16 * VS : 0);          // additive key mask: mask * -1e9, -inf beyond L
   int* live = reinterpret_cast<int*>(Ms + Lp);   // [ntiles] 1 if the 8-key tile holds an unmasked key
   int* lidx = live + ntiles;                     // [ntiles] compact list of live tiles
   // heads are the fastest-varying block index: the 8 CTAs of a state run side by side and share the 128-byte
   // lines / DRAM pages of its rows (a head only touches 64 B of each 1536 B qkv row)
   const int c = blockIdx.x >> 3, h = blockIdx.x & 7;
-  const int hg = h * 16;                       // this head's column offset in global memory
-  constexpr int hc = 0;                        // ... and in shared memory (only this head is staged)
+  const int hg = h * 16;
   const float* base = qkv + (size_t)c * L * 384;
-  stage_async(base, 384, 128 + hg, L, Lp, Ks);
-  stage_async(base, 384, 256 + hg, L, Lp, Vs);
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  ATTN_STAMP(0);
+  if (threadIdx.x == 0) kmax_bits = 0u;
   for (int j = threadIdx.x; j < Lp; j += blockDim.x)
     Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   __syncthreads();
-  mark_live_tiles(Ms, live, ntiles);   // the mask bookkeeping runs while the K / V copies are in flight
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const bool pv3x = L < 64;
-  const int nlive = compact_live(live, lidx, ntiles);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  for (int r0 = warp * 16; r0 < L; r0 += 64) {
-    uint32_t qh[2][4], ql[2][4];
+  ATTN_STAMP(1);
+  // stage K and V: two rows per thread in flight
+  float k2 = 0.f;
+  for (int j = threadIdx.x; j < Lp; j += 2 * blockDim.x) {
+    float4 kv[2][4], vv[2][4];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      uint32_t raw[4];
-      load_a_frag(base, 384, r0, L, hg + kk * 8, g, t, QSCALE, raw);
+    for (int u = 0; u < 2; ++u) {
+      const int jj = j + u * blockDim.x;
+      const float4* kp = reinterpret_cast<const float4*>(base + (size_t)min(jj, L - 1) * 384 + 128 + hg);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float x = __uint_as_float(raw[i]);
-        const float hi = tf32_rn(x);
-        qh[kk][i] = __float_as_uint(hi);
-        ql[kk][i] = __float_as_uint(x - hi);
+      for (int q = 0; q < 4; ++q) {
+        kv[u][q] = jj < L ? kp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        vv[u][q] = jj < L ? kp[32 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // ---- pass 1: row maxima
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 2
-    for (int li = 0; li < nlive; ++li) {
-      const int nt = lidx[li];
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
-      mma_tf32(s, qh[0][0], qh[0][1], qh[0][2], qh[0][3], tfbits(kr[0]), tfbits(kr[4]));
-      mma_tf32(s, qh[1][0], qh[1][1], qh[1][2], qh[1][3], tfbits(kr[8]), tfbits(kr[12]));
-      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-      mx0 = fmaxf(mx0, fmaxf(s[0] + ma, s[1] + mb));
-      mx1 = fmaxf(mx1, fmaxf(s[2] + ma, s[3] + mb));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    // ---- pass 2: exact scores, softmax numerators, P.V
-    float sum0 = 0.f, sum1 = 0.f;
-    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 2
-    for (int li = 0; li < nlive; ++li) {
-      const int nt = lidx[li];
-      float s[4] = {-mx0, -mx0, -mx1, -mx1};     // accumulate score - rowmax directly
-      const float* kr = Ks + (nt * 8 + g) * KS + hc + t;
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const float k0 = kr[kk * 8], k1 = kr[kk * 8 + 4];
-        const float k0h = tf32_rn(k0), k1h = tf32_rn(k1);
-        const uint32_t b0h = __float_as_uint(k0h), b1h = __float_as_uint(k1h);
-        const uint32_t b0l = __float_as_uint(k0 - k0h), b1l = __float_as_uint(k1 - k1h);
-        mma_tf32(s, ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3], b0h, b1h);
-        mma_tf32(s, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], b0l, b1l);
-        mma_tf32(s, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], b0h, b1h);
-      }
-      const float ma = Ms[nt * 8 + 2 * t], mb = Ms[nt * 8 + 2 * t + 1];
-      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + mb);
-      const float p2 = ex2(s[2] + ma), p3 = ex2(s[3] + mb);
-      sum0 += p0 + p1;
-      sum1 += p2 + p3;
-      // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
-      const float* v0 = Vs + (nt * 8 + 2 * t) * KS + hc + g;
-      if (pv3x) {
-        // short sequences: 3xTF32 again (with few keys there is no averaging of the operand rounding)
-        const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
-        const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
-        const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
+    for (int u = 0; u < 2; ++u) {
+      const int jj = j + u * blockDim.x;
+      if (jj >= Lp) continue;
+      store_k_row(Kc + jj * KC, kv[u]);
+      const float x[16] = {vv[u][0].x, vv[u][0].y, vv[u][0].z, vv[u][0].w, vv[u][1].x, vv[u][1].y, vv[u][1].z, vv[u][1].w,
+                           vv[u][2].x, vv[u][2].y, vv[u][2].z, vv[u][2].w, vv[u][3].x, vv[u][3].y, vv[u][3].z, vv[u][3].w};
 #pragma unroll
-        for (int n2 = 0; n2 < 2; ++n2) {
-          const float va = v0[n2 * 8], vb = v0[KS + n2 * 8];
-          const float vah = tf32_rn(va), vbh = tf32_rn(vb);
-          mma_tf32(o[n2], l0, l1, l2, l3, fbits(vah), fbits(vbh));
-          mma_tf32(o[n2], a0, a1, a2, a3, fbits(va - vah), fbits(vb - vbh));
-          mma_tf32(o[n2], a0, a1, a2, a3, fbits(vah), fbits(vbh));
-        }
-      } else {
-        const uint32_t a0 = tfbits(p0), a1 = tfbits(p2), a2 = tfbits(p1), a3 = tfbits(p3);
-        mma_tf32(o[0], a0, a1, a2, a3, tfbits(v0[0]), tfbits(v0[KS]));
-        mma_tf32(o[1], a0, a1, a2, a3, tfbits(v0[8]), tfbits(v0[KS + 8]));
+      for (int d = 0; d < 16; ++d) {
+        const float hi = tf32_rn(x[d]);
+        Vt[d * VS + jj] = hi;
+        if (PV3X) Vl[d * VS + jj] = x[d] - hi;
       }
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float i0 = 1.f / sum0, i1 = 1.f / sum1;
-    const int ra = r0 + g, rb = r0 + g + 8;
-    if (ra < L) {
-      float* dst = att + ((size_t)c * L + ra) * 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(o[0][0] * i0, o[0][1] * i0);
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][0] * i0, o[1][1] * i0);
-      if (t == 0 && lse) lse[((size_t)c * L + ra) * 8 + h] = mx0 * LN2 + logf(sum0);   // natural-log units
-    }
-    if (rb < L) {
-      float* dst = att + ((size_t)c * L + rb) * 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(o[0][2] * i1, o[0][3] * i1);
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(o[1][2] * i1, o[1][3] * i1);
-      if (t == 0 && lse) lse[((size_t)c * L + rb) * 8 + h] = mx1 * LN2 + logf(sum1);
+      float n2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        n2 += kv[u][q].x * kv[u][q].x + kv[u][q].y * kv[u][q].y + kv[u][q].z * kv[u][q].z + kv[u][q].w * kv[u][q].w;
+      k2 = fmaxf(k2, n2);
     }
   }
+  ATTN_STAMP(2);
+  k2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(k2)));   // non-negative floats order as uints
+  if (lane == 0) atomicMax(&kmax_bits, __float_as_uint(k2));
+  mark_live_tiles(Ms, live, ntiles);
+  __syncthreads();
+  const int nlive = compact_live(live, lidx, ntiles);   // (barrier inside: Kc / Vt / kmax are visible after it)
+  const float kmax2 = __uint_as_float(kmax_bits);
+  float* att_c = att + (size_t)c * L * 128;
+  float* lse_c = lse ? lse + (size_t)c * L * 8 : nullptr;
+
+  ATTN_STAMP(3);
+  // Warp w always runs on SM sub-partition w % 4, and the first warps of a CTA get the extra row block when the
+  // block count is not a multiple of 4: rotate the assignment per CTA so the sub-partitions stay evenly loaded.
+  int r0 = ((warp + ((blockIdx.x * 0x9E3779B1u) >> 30)) & 3) * 16;
+  for (; r0 + 64 < L; r0 += 128)
+    fwd_row_blocks<2, PV3X>(base, r0, L, hg, h, g, t, Kc, Vt, Vl, VS, Ms, lidx, nlive, kmax2, att_c, lse_c);
+  ATTN_STAMP(4);
+  if (r0 < L) fwd_row_blocks<1, PV3X>(base, r0, L, hg, h, g, t, Kc, Vt, Vl, VS, Ms, lidx, nlive, kmax2, att_c, lse_c);
+  ATTN_STAMP(5);
+  __syncthreads();
+  ATTN_STAMP(6);
 }
 
 // Backward (plain TF32). One CTA of 4 warps per (state, head); Q, K, V, dO of the head are staged once in shared
@@ -272,6 +422,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int hg = h * 16;
 
+  ATTN_STAMP(0);
   stage_async(base, 384, hg, L, Lr, Qs);
   stage_async(base, 384, 128 + hg, L, Lr, Ks);
   stage_async(base, 384, 256 + hg, L, Lr, Vs);
@@ -296,14 +447,17 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     Ds[i] = d;
     Ls[i] = l;
   }
+  ATTN_STAMP(1);
   __syncthreads();
   mark_live_tiles(Ms, live, ntiles);   // the mask bookkeeping runs while the copies are in flight
   __syncthreads();
   LiveBits lbits;
   lbits.load(live, ntiles);
   const int nlive = compact_live(live, lidx, ntiles);
+  ATTN_STAMP(2);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  ATTN_STAMP(3);
 
   // ---------------- phase A: dQ = dS K / 4 ----------------
   for (int r0 = warp * 16; r0 < L; r0 += 64) {
@@ -348,6 +502,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     }
   }
 
+  ATTN_STAMP(4);
   // ---------------- phase B: dK = dS^T Q / 4, dV = P^T dO (tile rows are KEYS, columns are QUERIES) ----------------
   for (int j0 = warp * 16; j0 < L; j0 += 64) {
     uint32_t ka[2][4], va[2][4];
@@ -399,6 +554,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
       *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][2]), tf32_rn(dv[1][3]));
     }
   }
+  ATTN_STAMP(5);
+  __syncthreads();
+  ATTN_STAMP(6);
 }
 
 }  // namespace
@@ -408,13 +566,16 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 1024) return TPC_ERR_SHAPE;
   const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(2 * Lp * KS + Lp + 2 * (Lp / 8) + 8) * sizeof(float);   // ~26 KB at L = 151: 8 CTAs / SM
-  static size_t attr_smem = 0;   // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
-  if (smem > attr_smem) {
-    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  const size_t smem = (size_t)(Lp * KC + (L < 64 ? 32 : 16) * vt_stride(Lp) + Lp + 2 * (Lp / 8) + 8) * sizeof(float);
+  // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
+  static size_t attr_smem[2] = {0, 0};
+  const int v = L < 64 ? 1 : 0;
+  auto kern = v ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  if (smem > attr_smem[v]) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[v] = smem;
   }
-  attn_fwd_kernel<<<C * 8, 128, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
+  kern<<<C * 8, 128, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
