@@ -6,6 +6,8 @@
 //
 // head_dim = 16 makes each head a K=16 contraction: far too thin for a 128-row tcgen05 tile, so
 // this stays a warp-level kernel; the 128-wide projections around it are the tcgen05 GEMMs in gemm_tc.cu.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace tpc {
@@ -120,89 +122,142 @@ struct LiveBits {
   __device__ __forceinline__ bool test(int nt) const { return nt >= 64 || ((w >> nt) & 1ull); }
 };
 
-// ---- forward operand images in shared memory ----
-// Kc[key][KC]: the key's 16 values as TF32 hi (floats 0..15) and lo = k - hi (16..31), each 8-column group stored
-// as (c0, c4, c1, c5, c2, c6, c3, c7) so the B fragment pair (k = t, k = t + 4) of an m16n8k8 MMA is one LDS.64.
-// Vt[d][VS]: V transposed and rounded, so the P.V fragment pair (keys 2t, 2t + 1) is one LDS.64 as well.
-// The strides (40, VS mod 32 in {8, 24}) keep both half-warp access patterns bank-conflict free.
-constexpr int KC = 40;
+// ---- operand images in shared memory ----
+// The legacy tensor path issues one MMA per ~8.7 clocks per SM sub-partition whatever its shape, and that pipe is
+// what bounds these kernels. Contractions over the 16-wide head dimension therefore use FP16 m16n8k16 (one MMA for
+// all 16 dims; FP16 carries the same 11 significand bits as TF32): rows are first scaled by a per-CTA power of two
+// so every element is <= 1 in magnitude (no overflow; elements far below the row maximum lose only absolute
+// precision 2^-25), and split hi + lo for the 3-MMA "fp32-level" product q.k = ql.kh + qh.kl + qh.kh.
+// Row image (16 words per row): for t = 0..3: [hi(2t,2t+1) hi(2t+8,2t+9) lo(2t,2t+1) lo(2t+8,2t+9)], i.e. lane
+// (g, t) gets its whole A or B fragment pair, hi and lo, with one conflict-free LDS.128.
+// Vt[d][VS]: V transposed and TF32-rounded, so the P.V fragment pair (keys 2t, 2t + 1) is one LDS.64 (the
+// contraction over keys stays TF32 m16n8k8: P can span the whole fp32 exponent range).
 __host__ __device__ inline int vt_stride(int Lp) { return (Lp % 32 == 0 || Lp % 32 == 16) ? Lp + 8 : Lp; }
 // scores are kept in log2 units; when |q| * max|k| stays below this bound the softmax needs no row-max pass
 // (2^s can neither overflow nor lose a term to underflow, and p / sum is scale invariant in floating point)
 constexpr float EASY_BOUND = 96.f;
 
-__device__ __forceinline__ void store_k_row(float* row, const float4 (&k)[4]) {
-  const float x[16] = {k[0].x, k[0].y, k[0].z, k[0].w, k[1].x, k[1].y, k[1].z, k[1].w,
-                       k[2].x, k[2].y, k[2].z, k[2].w, k[3].x, k[3].y, k[3].z, k[3].w};
-  float hi[16], lo[16];
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1, float c0, float c1, float c2, float c3) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+// 2^-e with sqrt(n2) * 2^-e <= 1 (n2 = largest squared row norm, so every element is covered), and its inverse
+__device__ __forceinline__ void pow2_scale(float n2, float& down, float& up) {
+  int ex = 0;
+  frexpf(n2, &ex);                     // n2 = m 2^ex, m in [0.5, 1)  ->  sqrt(n2) < 2^ceil(ex / 2)
+  int e = (ex + 1) >> 1;
+  e = max(-100, min(100, e));          // (inf / NaN / denormal norms: keep the scale finite)
+  down = __int_as_float((127 - e) << 23);
+  up = __int_as_float((127 + e) << 23);
+}
+// hi / lo FP16 row image of 16 scaled values
+__device__ __forceinline__ void store_split_row(uint32_t* row, const float4 (&v)[4], float scale) {
+  const float x[16] = {v[0].x * scale, v[0].y * scale, v[0].z * scale, v[0].w * scale, v[1].x * scale, v[1].y * scale,
+                       v[1].z * scale, v[1].w * scale, v[2].x * scale, v[2].y * scale, v[2].z * scale, v[2].w * scale,
+                       v[3].x * scale, v[3].y * scale, v[3].z * scale, v[3].w * scale};
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    hi[i] = tf32_rn(x[i]);
-    lo[i] = x[i] - hi[i];
-  }
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    const int o = kk * 8;
-    *reinterpret_cast<float4*>(row + o) = make_float4(hi[o], hi[o + 4], hi[o + 1], hi[o + 5]);
-    *reinterpret_cast<float4*>(row + o + 4) = make_float4(hi[o + 2], hi[o + 6], hi[o + 3], hi[o + 7]);
-    *reinterpret_cast<float4*>(row + 16 + o) = make_float4(lo[o], lo[o + 4], lo[o + 1], lo[o + 5]);
-    *reinterpret_cast<float4*>(row + 16 + o + 4) = make_float4(lo[o + 2], lo[o + 6], lo[o + 3], lo[o + 7]);
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t h0 = pack_h2(x[2 * t], x[2 * t + 1]), h1 = pack_h2(x[2 * t + 8], x[2 * t + 9]);
+    const float2 f0 = unpack_h2(h0), f1 = unpack_h2(h1);
+    const uint32_t l0 = pack_h2(x[2 * t] - f0.x, x[2 * t + 1] - f0.y);
+    const uint32_t l1 = pack_h2(x[2 * t + 8] - f1.x, x[2 * t + 9] - f1.y);
+    *reinterpret_cast<uint4*>(row + 4 * t) = make_uint4(h0, h1, l0, l1);
   }
 }
+// Q rows go to a fragment-major image: per 16-row block, hi[lane][4] then lo[lane][4] (lane = g * 4 + t of the MMA
+// A fragment: a0 = (row g, dims 2t, 2t+1), a1 = (row g + 8, same), a2 = (row g, dims 2t + 8, 2t + 9), a3 = (row g + 8, ...)),
+// so a lane's quad is one LDS.128 landing in consecutive registers (no per-MMA register shuffling).
+__device__ __forceinline__ void store_split_row_frag(uint32_t* img, int r, const float4 (&v)[4], float scale) {
+  const float x[16] = {v[0].x * scale, v[0].y * scale, v[0].z * scale, v[0].w * scale, v[1].x * scale, v[1].y * scale,
+                       v[1].z * scale, v[1].w * scale, v[2].x * scale, v[2].y * scale, v[2].z * scale, v[2].w * scale,
+                       v[3].x * scale, v[3].y * scale, v[3].z * scale, v[3].w * scale};
+  const int g = r & 7, half = (r >> 3) & 1;
+  uint32_t* blk = img + (r >> 4) * 256 + g * 16 + half;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t h0 = pack_h2(x[2 * t], x[2 * t + 1]), h1 = pack_h2(x[2 * t + 8], x[2 * t + 9]);
+    const float2 f0 = unpack_h2(h0), f1 = unpack_h2(h1);
+    blk[t * 4] = h0;
+    blk[t * 4 + 2] = h1;
+    blk[128 + t * 4] = pack_h2(x[2 * t] - f0.x, x[2 * t + 1] - f0.y);
+    blk[128 + t * 4 + 2] = pack_h2(x[2 * t + 8] - f1.x, x[2 * t + 9] - f1.y);
+  }
+}
+__device__ __forceinline__ float norm2(const float4 (&v)[4]) {
+  float n = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) n += v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+  return n;
+}
+// ordered list of the live 8-key tiles (a tile is live if it holds an unmasked key), built by one warp with ballots.
+// A masked key contributes exp(-1e9 - max) == 0 exactly in fp32, so dead tiles are skipped: exact, and
+// during an episode a third to a half of the keys (placed rules, full nodes) are masked. If nothing is unmasked
+// (cannot happen on the reference's trajectories) every tile stays live and the arithmetic degenerates to the
+// reference's uniform softmax over equal -1e9 logits.
+__device__ __forceinline__ void build_live_list(const float* Ms, int* lidx, int* n_out, int ntiles, int lane) {
+  int n = 0;
+  for (int nt0 = 0; nt0 < ntiles; nt0 += 32) {
+    const int nt = nt0 + lane;
+    bool l = false;
+    if (nt < ntiles) {
+      const float4 m0 = *reinterpret_cast<const float4*>(Ms + nt * 8), m1 = *reinterpret_cast<const float4*>(Ms + nt * 8 + 4);
+      l = m0.x == 0.f || m0.y == 0.f || m0.z == 0.f || m0.w == 0.f || m1.x == 0.f || m1.y == 0.f || m1.z == 0.f || m1.w == 0.f;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, l);
+    if (l) lidx[n + __popc(bal & ((1u << lane) - 1u))] = nt;
+    n += __popc(bal);
+  }
+  if (n == 0) {
+    for (int nt = lane; nt < ntiles; nt += 32) lidx[nt] = nt;
+    n = ntiles;
+  }
+  if (lane == 0) *n_out = n;
+}
 
-// RB 16-row query blocks (rows r0 + 64 b) of one warp against all live key tiles. The blocks share every K / V
-// fragment load and give the scheduler RB independent MMA chains: the loop is latency bound, not issue bound.
-template <int RB, bool PV3X>
-__device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, int r0, int L, int hg, int h, int g, int t,
-                                               const float* Kc, const float* Vt, const float* Vl, int VS,
-                                               const float* Ms, const int* lidx, int nlive, float kmax2,
+// RB 16-row query blocks (rows r0 + rstride b) of one warp against all live key tiles. The blocks share every K / V
+// fragment load and give the scheduler RB independent MMA chains.
+template <int RB, bool PV3X, bool EASY>
+__device__ __forceinline__ void fwd_row_blocks(int r0, int rstride, int L, int hg, int h, int g, int t, const uint32_t* Qi,
+                                               const uint32_t* Ki, const float* Vt, const float* Vl, int VS,
+                                               const float* Ms, const int* lidx, int nlive, float sc_mul,
                                                float* __restrict__ att_c, float* __restrict__ lse_c) {
-  uint32_t qh[RB][2][4], ql[RB][2][4];
-  float q2 = 0.f;
+  // A fragments: the Q image is fragment-major, one LDS.128 is the whole register quad of a lane
+  uint32_t qh[RB][4], ql[RB][4];
 #pragma unroll
   for (int b = 0; b < RB; ++b) {
-    float qa2 = 0.f, qb2 = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      uint32_t raw[4];
-      load_a_frag(base, 384, r0 + 64 * b, L, hg + kk * 8, g, t, QSCALE, raw);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float x = __uint_as_float(raw[i]);
-        const float hi = tf32_rn(x);
-        qh[b][kk][i] = __float_as_uint(hi);
-        ql[b][kk][i] = __float_as_uint(x - hi);
-        if (i & 1) qb2 = fmaf(x, x, qb2); else qa2 = fmaf(x, x, qa2);
-      }
-    }
-    // |q|^2 of the block's rows (4 lanes hold a row)
-    qa2 += __shfl_xor_sync(0xffffffffu, qa2, 1);
-    qa2 += __shfl_xor_sync(0xffffffffu, qa2, 2);
-    qb2 += __shfl_xor_sync(0xffffffffu, qb2, 1);
-    qb2 += __shfl_xor_sync(0xffffffffu, qb2, 2);
-    q2 = fmaxf(q2, fmaxf(qa2, qb2));
+    const uint32_t* qf = Qi + (r0 + rstride * b) * 16 + (g * 4 + t) * 4;
+    const uint4 hq = *reinterpret_cast<const uint4*>(qf), lq = *reinterpret_cast<const uint4*>(qf + 128);
+    qh[b][0] = hq.x, qh[b][1] = hq.y, qh[b][2] = hq.z, qh[b][3] = hq.w;
+    ql[b][0] = lq.x, ql[b][1] = lq.y, ql[b][2] = lq.z, ql[b][3] = lq.w;
   }
-  q2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(q2)));   // warp uniform
-  const bool easy = q2 * kmax2 < EASY_BOUND * EASY_BOUND;   // NaN / inf take the two-pass path
-  // ---- pass 1 (rare): row maxima
+  const uint32_t* kbase = Ki + g * 16 + 4 * t;
+  const float* vbase = Vt + g * VS + 2 * t;
+  const float* mbase = Ms + 2 * t;
+  // ---- pass 1 (rare): row maxima from the hi product
   float mx[RB][2];
 #pragma unroll
   for (int b = 0; b < RB; ++b) mx[b][0] = mx[b][1] = 0.f;
-  if (!easy) {
+  if (!EASY) {
 #pragma unroll
     for (int b = 0; b < RB; ++b) mx[b][0] = mx[b][1] = -INFINITY;
     for (int li = 0; li < nlive; ++li) {
       const int nt = lidx[li];
-      const float* kr = Kc + (nt * 8 + g) * KC + 2 * t;
-      const float2 h0 = *reinterpret_cast<const float2*>(kr), h1 = *reinterpret_cast<const float2*>(kr + 8);
-      const float2 mk = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
+      const uint2 kh = *reinterpret_cast<const uint2*>(kbase + nt * 128);
+      const float2 mk = *reinterpret_cast<const float2*>(mbase + nt * 8);
 #pragma unroll
       for (int b = 0; b < RB; ++b) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(s, qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(h0.x), fbits(h0.y));
-        mma_tf32(s, qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(h1.x), fbits(h1.y));
-        mx[b][0] = fmaxf(mx[b][0], fmaxf(s[0] + mk.x, s[1] + mk.y));
-        mx[b][1] = fmaxf(mx[b][1], fmaxf(s[2] + mk.x, s[3] + mk.y));
+        float s[4];
+        mma_f16(s, qh[b][0], qh[b][1], qh[b][2], qh[b][3], kh.x, kh.y, 0.f, 0.f, 0.f, 0.f);
+        mx[b][0] = fmaxf(mx[b][0], fmaxf(fmaf(s[0], sc_mul, mk.x), fmaf(s[1], sc_mul, mk.y)));
+        mx[b][1] = fmaxf(mx[b][1], fmaxf(fmaf(s[2], sc_mul, mk.x), fmaf(s[3], sc_mul, mk.y)));
       }
     }
 #pragma unroll
@@ -221,15 +276,10 @@ __device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, i
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[b][0][i] = o[b][1][i] = 0.f;
   }
-  const float* kbase = Kc + g * KC + 2 * t;
-  const float* vbase = Vt + g * VS + 2 * t;
-  const float* mbase = Ms + 2 * t;
 #pragma unroll 2
   for (int li = 0; li < nlive; ++li) {
     const int nt = lidx[li];
-    const float* kr = kbase + nt * (8 * KC);
-    const float2 kh0 = *reinterpret_cast<const float2*>(kr), kh1 = *reinterpret_cast<const float2*>(kr + 8);
-    const float2 kl0 = *reinterpret_cast<const float2*>(kr + 16), kl1 = *reinterpret_cast<const float2*>(kr + 24);
+    const uint4 kf = *reinterpret_cast<const uint4*>(kbase + nt * 128);   // kh(b0, b1), kl(b0, b1)
     const float2 mk = *reinterpret_cast<const float2*>(mbase + nt * 8);
     // P as A operand with its k index relabelled (k=t <-> key 2t, k=t+4 <-> key 2t+1): no shuffles needed.
     const float* vr = vbase + nt * 8;
@@ -240,32 +290,26 @@ __device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, i
       w1 = *reinterpret_cast<const float2*>(vr + (Vl - Vt) + 8 * VS);
     }
     float sc[RB][4];
-#pragma unroll
-    for (int b = 0; b < RB; ++b) {
-      sc[b][0] = sc[b][1] = -mx[b][0];     // accumulate score - rowmax directly
-      sc[b][2] = sc[b][3] = -mx[b][1];
-    }
     // small terms first; the RB chains are independent and interleave
 #pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], ql[b][0][0], ql[b][0][1], ql[b][0][2], ql[b][0][3], fbits(kh0.x), fbits(kh0.y));
+    for (int b = 0; b < RB; ++b) mma_f16(sc[b], ql[b][0], ql[b][1], ql[b][2], ql[b][3], kf.x, kf.y, 0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(kl0.x), fbits(kl0.y));
+    for (int b = 0; b < RB; ++b)
+      mma_f16(sc[b], qh[b][0], qh[b][1], qh[b][2], qh[b][3], kf.z, kf.w, sc[b][0], sc[b][1], sc[b][2], sc[b][3]);
 #pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], ql[b][1][0], ql[b][1][1], ql[b][1][2], ql[b][1][3], fbits(kh1.x), fbits(kh1.y));
-#pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(kl1.x), fbits(kl1.y));
-#pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][0][0], qh[b][0][1], qh[b][0][2], qh[b][0][3], fbits(kh0.x), fbits(kh0.y));
-#pragma unroll
-    for (int b = 0; b < RB; ++b) mma_tf32(sc[b], qh[b][1][0], qh[b][1][1], qh[b][1][2], qh[b][1][3], fbits(kh1.x), fbits(kh1.y));
+    for (int b = 0; b < RB; ++b)
+      mma_f16(sc[b], qh[b][0], qh[b][1], qh[b][2], qh[b][3], kf.x, kf.y, sc[b][0], sc[b][1], sc[b][2], sc[b][3]);
 #pragma unroll
     for (int b = 0; b < RB; ++b) {
-      const float p0 = ex2(sc[b][0] + mk.x), p1 = ex2(sc[b][1] + mk.y);
-      const float p2 = ex2(sc[b][2] + mk.x), p3 = ex2(sc[b][3] + mk.y);
+      // (rare two-pass path: the row maximum is folded into the additive mask term)
+      const float ma0 = EASY ? mk.x : mk.x - mx[b][0], ma1 = EASY ? mk.y : mk.y - mx[b][0];
+      const float mb0 = EASY ? mk.x : mk.x - mx[b][1], mb1 = EASY ? mk.y : mk.y - mx[b][1];
+      const float p0 = ex2(fmaf(sc[b][0], sc_mul, ma0)), p1 = ex2(fmaf(sc[b][1], sc_mul, ma1));
+      const float p2 = ex2(fmaf(sc[b][2], sc_mul, mb0)), p3 = ex2(fmaf(sc[b][3], sc_mul, mb1));
       sum[b][0] += p0 + p1;
       sum[b][1] += p2 + p3;
       if (PV3X) {
-        // short sequences: 3xTF32 again (with few keys there is no averaging of the operand rounding)
+        // short sequences: 3xTF32 (with few keys there is no averaging of the operand rounding)
         const float h0 = tf32_rn(p0), h1 = tf32_rn(p2), h2 = tf32_rn(p1), h3 = tf32_rn(p3);
         const uint32_t a0 = fbits(h0), a1 = fbits(h1), a2 = fbits(h2), a3 = fbits(h3);
         const uint32_t l0 = fbits(p0 - h0), l1 = fbits(p2 - h1), l2 = fbits(p1 - h2), l3 = fbits(p3 - h3);
@@ -290,7 +334,7 @@ __device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, i
       sm_ += __shfl_xor_sync(0xffffffffu, sm_, 1);
       sm_ += __shfl_xor_sync(0xffffffffu, sm_, 2);
       const float inv = 1.f / sm_;
-      const int row = r0 + 64 * b + g + 8 * r;
+      const int row = r0 + rstride * b + g + 8 * r;
       if (row < L) {
         float* dst = att_c + (size_t)row * 128 + hg + 2 * t;
         *reinterpret_cast<float2*>(dst) = make_float2(o[b][0][2 * r] * inv, o[b][0][2 * r + 1] * inv);
@@ -301,93 +345,144 @@ __device__ __forceinline__ void fwd_row_blocks(const float* __restrict__ base, i
   }
 }
 
-// Forward: one CTA of 4 warps per (state, head); ~35 KB of smem at 151 tokens, so 5-6 CTAs share an SM and one
-// CTA's staging latency hides behind the others' math; the warps take alternating 16-row query blocks, two at a time.
-// Scores are 3xTF32 (hi/lo split of Q and K: fp32-level logits, the softmax amplifies score errors); P.V is plain
-// TF32 with P, V rounded to nearest (3xTF32 below 64 tokens, where there is no averaging of the rounding).
-// The row maximum is only searched (pass 1) when the norm bound says the exponentials could leave fp32 range.
+constexpr int FWD_WARPS = 4;
+constexpr int FWD_THREADS = FWD_WARPS * 32;
+constexpr int RS = 20;   // raw (cp.async) row stride in floats: 16 of one head + 4, conflict-free float4 row reads
+
+// cp.async of the head's 16 columns of rows [0, L) of matrix m (Q, K, V = column blocks 0, 1, 2 of qkv) into raw
+__device__ __forceinline__ void prefetch_rows(const float* __restrict__ src, int ld, int L, float* raw) {
+  for (int idx = threadIdx.x; idx < 4 * L; idx += blockDim.x) {
+    const int r = idx >> 2, c4 = idx & 3;
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(raw + r * RS + c4 * 4));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)r * ld + c4 * 4) : "memory");
+  }
+}
+__device__ __forceinline__ void prefetch_mask(const float* __restrict__ src, int L, float* raw) {
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(raw + j));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + j) : "memory");
+  }
+}
+__device__ __forceinline__ void raw_row(const float* raw, int r, int L, float4 (&x)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    x[q] = r < L ? *reinterpret_cast<const float4*>(raw + r * RS + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Forward: persistent CTAs of 4 warps, each looping over (state, head) items (heads fastest, so the CTAs in flight
+// share the 128-byte lines / DRAM pages of a state's rows: a head only touches 64 B of each 1536 B qkv row).
+// Per item: the raw Q / K / V rows and the mask arrive by cp.async (issued one item ahead, so the global latency
+// hides behind the previous item's math), are converted into the operand images, and the rest only touches shared
+// memory. The warps take alternating 16-row query blocks, two at a time. Scores are the 3-MMA FP16 split product
+// (fp32-level logits: the softmax amplifies score errors); P.V is plain TF32 with P, V rounded to nearest (3xTF32
+// below 64 tokens, where there is no averaging of the rounding). The row maximum is only searched (pass 1) when
+// the norm bound says the exponentials could leave fp32 range.
 template <bool PV3X>
-__global__ void __launch_bounds__(128, 5) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
-                                                          int mS, int m0, int L, float* __restrict__ att,
+__global__ void __launch_bounds__(FWD_THREADS, 3) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                          int mS, int m0, int L, int nitems, float* __restrict__ att,
                                                           float* __restrict__ lse) {
   extern __shared__ float sm[];
-  __shared__ unsigned kmax_bits;
+  __shared__ unsigned nrm_bits[2][2];   // [item parity][Q, K]: largest squared row norm (non-negative floats order as uints)
+  __shared__ int n_live_s;
   const int ntiles = (L + 7) >> 3;
   const int Lp = ntiles * 8;
+  const int Lr = (Lp + 15) & ~15;    // query rows staged (A fragments read 16-row blocks)
   const int VS = vt_stride(Lp);
-  float* Kc = sm;
-  float* Vt = Kc + Lp * KC;
+  uint32_t* Qi = reinterpret_cast<uint32_t*>(sm);   // [Lr][16]
+  uint32_t* Ki = Qi + Lr * 16;                      // [Lp][16]
+  float* Vt = reinterpret_cast<float*>(Ki + Lp * 16);
   float* Vl = Vt + 16 * VS;                       // lo part of V, only when PV3X
   float* Ms = Vl + (PV3X ? 16 * VS : 0);          // additive key mask: mask * -1e9, -inf beyond L
-  int* live = reinterpret_cast<int*>(Ms + Lp);   // [ntiles] 1 if the 8-key tile holds an unmasked key
-  int* lidx = live + ntiles;                     // [ntiles] compact list of live tiles
-  // heads are the fastest-varying block index: the 8 CTAs of a state run side by side and share the 128-byte
-  // lines / DRAM pages of its rows (a head only touches 64 B of each 1536 B qkv row)
-  const int c = blockIdx.x >> 3, h = blockIdx.x & 7;
-  const int hg = h * 16;
-  const float* base = qkv + (size_t)c * L * 384;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  ATTN_STAMP(0);
-  if (threadIdx.x == 0) kmax_bits = 0u;
-  for (int j = threadIdx.x; j < Lp; j += blockDim.x)
-    Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
-  __syncthreads();
-  ATTN_STAMP(1);
-  // stage K and V: two rows per thread in flight
-  float k2 = 0.f;
-  for (int j = threadIdx.x; j < Lp; j += 2 * blockDim.x) {
-    float4 kv[2][4], vv[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int jj = j + u * blockDim.x;
-      const float4* kp = reinterpret_cast<const float4*>(base + (size_t)min(jj, L - 1) * 384 + 128 + hg);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        kv[u][q] = jj < L ? kp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        vv[u][q] = jj < L ? kp[32 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int jj = j + u * blockDim.x;
-      if (jj >= Lp) continue;
-      store_k_row(Kc + jj * KC, kv[u]);
-      const float x[16] = {vv[u][0].x, vv[u][0].y, vv[u][0].z, vv[u][0].w, vv[u][1].x, vv[u][1].y, vv[u][1].z, vv[u][1].w,
-                           vv[u][2].x, vv[u][2].y, vv[u][2].z, vv[u][2].w, vv[u][3].x, vv[u][3].y, vv[u][3].z, vv[u][3].w};
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float hi = tf32_rn(x[d]);
-        Vt[d * VS + jj] = hi;
-        if (PV3X) Vl[d * VS + jj] = x[d] - hi;
-      }
-      float n2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        n2 += kv[u][q].x * kv[u][q].x + kv[u][q].y * kv[u][q].y + kv[u][q].z * kv[u][q].z + kv[u][q].w * kv[u][q].w;
-      k2 = fmaxf(k2, n2);
-    }
-  }
-  ATTN_STAMP(2);
-  k2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(k2)));   // non-negative floats order as uints
-  if (lane == 0) atomicMax(&kmax_bits, __float_as_uint(k2));
-  mark_live_tiles(Ms, live, ntiles);
-  __syncthreads();
-  const int nlive = compact_live(live, lidx, ntiles);   // (barrier inside: Kc / Vt / kmax are visible after it)
-  const float kmax2 = __uint_as_float(kmax_bits);
-  float* att_c = att + (size_t)c * L * 128;
-  float* lse_c = lse ? lse + (size_t)c * L * 8 : nullptr;
+  int* lidx = reinterpret_cast<int*>(Ms + Lp);   // [ntiles] ordered list of live tiles
+  float* raw = reinterpret_cast<float*>(lidx + ((ntiles + 3) & ~3));   // [3][Lp][RS] rows as they are in qkv (16 B aligned)
+  float* Mraw = raw + 3 * Lp * RS;               // [Lp] the 0/1 mask row
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
-  ATTN_STAMP(3);
-  // Warp w always runs on SM sub-partition w % 4, and the first warps of a CTA get the extra row block when the
-  // block count is not a multiple of 4: rotate the assignment per CTA so the sub-partitions stay evenly loaded.
-  int r0 = ((warp + ((blockIdx.x * 0x9E3779B1u) >> 30)) & 3) * 16;
-  for (; r0 + 64 < L; r0 += 128)
-    fwd_row_blocks<2, PV3X>(base, r0, L, hg, h, g, t, Kc, Vt, Vl, VS, Ms, lidx, nlive, kmax2, att_c, lse_c);
-  ATTN_STAMP(4);
-  if (r0 < L) fwd_row_blocks<1, PV3X>(base, r0, L, hg, h, g, t, Kc, Vt, Vl, VS, Ms, lidx, nlive, kmax2, att_c, lse_c);
-  ATTN_STAMP(5);
-  __syncthreads();
-  ATTN_STAMP(6);
+  auto prefetch = [&](int item) {
+    const int c = item >> 3, hg = (item & 7) * 16;
+    const float* base = qkv + (size_t)c * L * 384 + hg;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) prefetch_rows(base + m * 128, 384, L, raw + m * Lp * RS);
+    prefetch_mask(mask + (size_t)c * mS + m0, L, Mraw);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (tid < 4) (&nrm_bits[0][0])[tid] = 0u;
+  int item = blockIdx.x;
+  if (item < nitems) prefetch(item);
+  for (int it = 0; item < nitems; item += gridDim.x, ++it) {
+    const int c = item >> 3, h = item & 7, hg = h * 16, par = it & 1;
+    ATTN_STAMP(0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // raw rows of this item visible; every warp is done with the previous item's images
+    ATTN_STAMP(1);
+    for (int j = tid; j < Lp; j += FWD_THREADS) Ms[j] = j < L ? Mraw[j] * -BIG_NUMBER : -INFINITY;
+    float qn = 0.f, kn = 0.f;
+    for (int u = tid; u < 2 * Lp; u += FWD_THREADS) {
+      float4 x[4];
+      raw_row(raw + (u < Lp ? 0 : Lp * RS), u < Lp ? u : u - Lp, L, x);
+      const float n2 = norm2(x);
+      if (u < Lp) qn = fmaxf(qn, n2); else kn = fmaxf(kn, n2);
+    }
+    qn = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(qn)));
+    kn = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kn)));
+    if (lane == 0) {
+      atomicMax(&nrm_bits[par][0], __float_as_uint(qn));
+      atomicMax(&nrm_bits[par][1], __float_as_uint(kn));
+    }
+    ATTN_STAMP(2);
+    __syncthreads();
+    ATTN_STAMP(3);
+    if (warp == 0) build_live_list(Ms, lidx, &n_live_s, ntiles, lane);
+    if (tid < 2) nrm_bits[par ^ 1][tid] = 0u;   // for the next item (its atomics come after the next barrier)
+    const float q2max = __uint_as_float(nrm_bits[par][0]), k2max = __uint_as_float(nrm_bits[par][1]);
+    float q_down, q_up, k_down, k_up;
+    pow2_scale(q2max, q_down, q_up);
+    pow2_scale(k2max, k_down, k_up);
+    for (int u = tid; u < Lr + 2 * Lp; u += FWD_THREADS) {
+      float4 x[4];
+      if (u < Lr) {
+        raw_row(raw, u, L, x);
+        store_split_row_frag(Qi, u, x, q_down);
+      } else if (u < Lr + Lp) {
+        raw_row(raw + Lp * RS, u - Lr, L, x);
+        store_split_row(Ki + (u - Lr) * 16, x, k_down);
+      } else {
+        const int r = u - Lr - Lp;
+        raw_row(raw + 2 * Lp * RS, r, L, x);
+        const float v[16] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w,
+                             x[2].x, x[2].y, x[2].z, x[2].w, x[3].x, x[3].y, x[3].z, x[3].w};
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) {
+          const float hi = tf32_rn(v[dd]);
+          Vt[dd * VS + r] = hi;
+          if (PV3X) Vl[dd * VS + r] = v[dd] - hi;
+        }
+      }
+    }
+    ATTN_STAMP(4);
+    __syncthreads();   // images ready; raw is free again
+    if (item + (int)gridDim.x < nitems) prefetch(item + gridDim.x);
+    ATTN_STAMP(5);
+    const int nlive = n_live_s;
+    const float sc_mul = QSCALE * q_up * k_up;                                  // accumulator -> log2-unit score
+    const bool easy = q2max * k2max * (QSCALE * QSCALE) < EASY_BOUND * EASY_BOUND;   // NaN / inf: two-pass path
+    float* att_c = att + (size_t)c * L * 128;
+    float* lse_c = lse ? lse + (size_t)c * L * 8 : nullptr;
+    // Warp w always runs on SM sub-partition w % 4, and the first warps of a CTA get the extra row block when the
+    // block count is not a multiple of 4: rotate the assignment per item so the sub-partitions stay evenly loaded.
+    const int rot = ((warp + it) % FWD_WARPS) * 16, stride = FWD_WARPS * 16;
+    if (easy) {
+      int r0 = rot;
+      for (; r0 + stride < L; r0 += 2 * stride)
+        fwd_row_blocks<2, PV3X, true>(r0, stride, L, hg, h, g, t, Qi, Ki, Vt, Vl, VS, Ms, lidx, nlive, sc_mul, att_c, lse_c);
+      ATTN_STAMP(6);
+      if (r0 < L) fwd_row_blocks<1, PV3X, true>(r0, stride, L, hg, h, g, t, Qi, Ki, Vt, Vl, VS, Ms, lidx, nlive, sc_mul, att_c, lse_c);
+    } else {
+      for (int r0 = rot; r0 < L; r0 += stride)
+        fwd_row_blocks<1, PV3X, false>(r0, stride, L, hg, h, g, t, Qi, Ki, Vt, Vl, VS, Ms, lidx, nlive, sc_mul, att_c, lse_c);
+    }
+    ATTN_STAMP(7);
+  }
 }
 
 // Backward (plain TF32). One CTA of 4 warps per (state, head); Q, K, V, dO of the head are staged once in shared
@@ -564,18 +659,27 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
 int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
                   cudaStream_t st) {
   if (C <= 0) return TPC_OK;
-  if (L < 1 || L > 1024) return TPC_ERR_SHAPE;
-  const int Lp = ((L + 7) / 8) * 8;
-  const size_t smem = (size_t)(Lp * KC + (L < 64 ? 32 : 16) * vt_stride(Lp) + Lp + 2 * (Lp / 8) + 8) * sizeof(float);
+  if (L < 1 || L > 512) return TPC_ERR_SHAPE;
+  const int Lp = ((L + 7) / 8) * 8, Lr = (Lp + 15) & ~15, nt = Lp / 8;
+  const size_t smem = (size_t)((Lr + Lp) * 16 + (L < 64 ? 32 : 16) * vt_stride(Lp) + Lp + ((nt + 3) & ~3) + 3 * Lp * RS + Lp) *
+                      sizeof(float);
   // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
   static size_t attr_smem[2] = {0, 0};
+  static int ctas_per_sm[2] = {0, 0}, num_sms = 0;
   const int v = L < 64 ? 1 : 0;
   auto kern = v ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
-  if (smem > attr_smem[v]) {
+  if (smem > attr_smem[v] || ctas_per_sm[v] == 0) {
     TPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[v] = smem;
+    int dev = 0;
+    TPC_CHECK_CUDA(cudaGetDevice(&dev));
+    TPC_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[v], kern, FWD_THREADS, smem));
+    if (ctas_per_sm[v] < 1) return TPC_ERR_SHAPE;
   }
-  kern<<<C * 8, 128, smem, st>>>(qkv, mask, mS, m0, L, att, lse);
+  const int nitems = C * 8;
+  const int grid = nitems < num_sms * ctas_per_sm[v] ? nitems : num_sms * ctas_per_sm[v];
+  kern<<<grid, FWD_THREADS, smem, st>>>(qkv, mask, mS, m0, L, nitems, att, lse);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
