@@ -25,7 +25,6 @@ __device__ long long attn_prof[8 * 32768];
 #define ATTN_STAMP(i)
 #endif
 
-constexpr int KS = 20;   // smem row stride in floats (16 of one head + 4): conflict-free fragment loads
 constexpr float BIG_NUMBER = 1e9f;
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -47,87 +46,11 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float QSCALE = 0.25f * LOG2E;   // 1/sqrt(depth=16), scores kept in log2 units so that exp == one ex2
 __device__ __forceinline__ uint32_t tfbits(float x) { return tf32_rn_bits(x); }   // MMA truncates: add == round
 
-// Asynchronous staging (cp.async, 16 B, L1 bypass) of the 16 columns of one head of rows [0, Lr) into smem [Lr][KS];
-// rows >= L are zero-filled. All copies of a CTA are in flight together (one commit group): the kernels are bound
-// by this staging latency, not by the tile math (measured: removing the inner loops changes the time by < 30 %).
-__device__ __forceinline__ void stage_async(const float* __restrict__ src, int ld, int col0, int L, int Lr, float* dst) {
-  for (int idx = threadIdx.x; idx < Lr * 4; idx += blockDim.x) {
-    const int r = idx >> 2, c4 = idx & 3;
-    const float* g = src + (size_t)min(r, L - 1) * ld + col0 + c4 * 4;
-    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * KS + c4 * 4));
-    const int bytes = r < L ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
-  }
-}
-// A fragment (rows row_a / row_b, columns c0 + t and c0 + t + 4) from a staged smem tile, scaled, TF32-rounded bits
-__device__ __forceinline__ void lds_a_frag(const float* sm, int row_a, int row_b, int c0, int t, float scale,
-                                           uint32_t (&a)[4]) {
-  a[0] = tf32_rn_bits(sm[row_a * KS + c0 + t] * scale);
-  a[1] = tf32_rn_bits(sm[row_b * KS + c0 + t] * scale);
-  a[2] = tf32_rn_bits(sm[row_a * KS + c0 + t + 4] * scale);
-  a[3] = tf32_rn_bits(sm[row_b * KS + c0 + t + 4] * scale);
-}
-
-// A fragment (16 rows x 8 cols at column c0) of a global row-major matrix; rows clamped to L-1
-__device__ __forceinline__ void load_a_frag(const float* __restrict__ base, int ld, int r0, int L, int c0, int g, int t,
-                                            float scale, uint32_t (&a)[4]) {
-  const int ra = min(r0 + g, L - 1), rb = min(r0 + g + 8, L - 1);
-  a[0] = fbits(base[(size_t)ra * ld + c0 + t] * scale);
-  a[1] = fbits(base[(size_t)rb * ld + c0 + t] * scale);
-  a[2] = fbits(base[(size_t)ra * ld + c0 + t + 4] * scale);
-  a[3] = fbits(base[(size_t)rb * ld + c0 + t + 4] * scale);
-}
-
-// A masked key contributes exp(-1e9 - max) == 0 exactly in fp32, so 8-key tiles without any unmasked
-// key are skipped: exact, and during an episode a third to a half of the keys (placed rules, full nodes) are masked.
-// If nothing is unmasked (cannot happen on the reference's trajectories) every tile stays live and the arithmetic
-// degenerates to the reference's uniform softmax over equal -1e9 logits.
-__device__ __forceinline__ void mark_live_tiles(const float* Ms, int* live, int ntiles) {
-  __shared__ int any_live;
-  if (threadIdx.x == 0) any_live = 0;
-  __syncthreads();
-  for (int nt = threadIdx.x; nt < ntiles; nt += blockDim.x) {
-    int l = 0;
-    for (int j = 0; j < 8; ++j) l |= (Ms[nt * 8 + j] == 0.f);
-    live[nt] = l;
-    if (l) any_live = 1;
-  }
-  __syncthreads();
-  if (!any_live)
-    for (int nt = threadIdx.x; nt < ntiles; nt += blockDim.x) live[nt] = 1;
-}
-// compact, ordered list of the live tiles (branch-free inner loops that can be unrolled for ILP); returns the count
-__device__ __forceinline__ int compact_live(const int* live, int* idx, int ntiles) {
-  __shared__ int n_live;
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int nt = 0; nt < ntiles; ++nt)
-      if (live[nt]) idx[n++] = nt;
-    n_live = n;
-  }
-  __syncthreads();
-  return n_live;
-}
-// the flags as a register bit mask (tile nt -> bit nt); beyond 64 tiles (L > 512) nothing is skipped
-struct LiveBits {
-  unsigned long long w;
-  __device__ __forceinline__ void load(const int* live, int ntiles) {
-    w = ~0ull;
-    if (ntiles <= 64) {
-      w = 0ull;
-      for (int nt = 0; nt < ntiles; ++nt)
-        if (live[nt]) w |= 1ull << nt;
-    }
-  }
-  __device__ __forceinline__ bool test(int nt) const { return nt >= 64 || ((w >> nt) & 1ull); }
-};
-
 // ---- operand images in shared memory ----
 // The legacy tensor path issues one MMA per ~8.7 clocks per SM sub-partition whatever its shape, and that pipe is
 // what bounds these kernels. Contractions over the 16-wide head dimension therefore use FP16 m16n8k16 (one MMA for
 // all 16 dims; FP16 carries the same 11 significand bits as TF32): rows are first scaled by a per-CTA power of two
-// so every element is <= 1 in magnitude (no overflow; elements far below the row maximum lose only absolute
-// precision 2^-25), and split hi + lo for the 3-MMA "fp32-level" product q.k = ql.kh + qh.kl + qh.kh.
+// so every row norm is <= 2^14 (no overflow; elements 2^-28 below the largest row norm start to lose precision), and split hi + lo for the 3-MMA "fp32-level" product q.k = ql.kh + qh.kl + qh.kh.
 // Row image (16 words per row): for t = 0..3: [hi(2t,2t+1) hi(2t+8,2t+9) lo(2t,2t+1) lo(2t+8,2t+9)], i.e. lane
 // (g, t) gets its whole A or B fragment pair, hi and lo, with one conflict-free LDS.128.
 // Vt[d][VS]: V transposed and TF32-rounded, so the P.V fragment pair (keys 2t, 2t + 1) is one LDS.64 (the
@@ -149,11 +72,13 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
-// 2^-e with sqrt(n2) * 2^-e <= 1 (n2 = largest squared row norm, so every element is covered), and its inverse
-__device__ __forceinline__ void pow2_scale(float n2, float& down, float& up) {
+// Power-of-two scale `down` with sqrt(n2) * down <= 2^target (n2 = largest squared row norm, so every element is
+// covered), and its inverse. A target well above 1 keeps the lo parts / small elements out of FP16's subnormal range
+// (below 2^-14 only 2^-24 absolute precision is left); FP16 tops out at 65504 ~ 2^16.
+__device__ __forceinline__ void pow2_scale(float n2, int target, float& down, float& up) {
   int ex = 0;
   frexpf(n2, &ex);                     // n2 = m 2^ex, m in [0.5, 1)  ->  sqrt(n2) < 2^ceil(ex / 2)
-  int e = (ex + 1) >> 1;
+  int e = ((ex + 1) >> 1) - target;
   e = max(-100, min(100, e));          // (inf / NaN / denormal norms: keep the scale finite)
   down = __int_as_float((127 - e) << 23);
   up = __int_as_float((127 + e) << 23);
@@ -436,8 +361,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) attn_fwd_kernel(const float* _
     if (tid < 2) nrm_bits[par ^ 1][tid] = 0u;   // for the next item (its atomics come after the next barrier)
     const float q2max = __uint_as_float(nrm_bits[par][0]), k2max = __uint_as_float(nrm_bits[par][1]);
     float q_down, q_up, k_down, k_up;
-    pow2_scale(q2max, q_down, q_up);
-    pow2_scale(k2max, k_down, k_up);
+    pow2_scale(q2max, 14, q_down, q_up);
+    pow2_scale(k2max, 14, k_down, k_up);
     for (int u = tid; u < Lr + 2 * Lp; u += FWD_THREADS) {
       float4 x[4];
       if (u < Lr) {
@@ -485,173 +410,398 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) attn_fwd_kernel(const float* _
   }
 }
 
-// Backward (plain TF32). One CTA of 4 warps per (state, head); Q, K, V, dO of the head are staged once in shared
-// memory with cp.async (all copies in flight together) while D_i = sum_d dO[i][d] * O[i][d] and the log-sum-exp are
-// gathered from global memory. Phase A (query row blocks): dQ; phase B (key row blocks): dK, dV. P is recomputed
-// from the saved log-sum-exp. Accumulators start at the row constants (-lse, -D), so p = 2^(s + mask) and
-// dS = p * dp need no extra subtractions. Operands are rounded to TF32 with one integer add at fragment load.
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
-                                                       const float* __restrict__ lse, const float* __restrict__ datt,
-                                                       const float* __restrict__ mask, int mS, int m0, int L,
-                                                       float* __restrict__ dqkv) {
+// ------------------------------------------------------------------------------------------------------------------
+// Backward. All five products run as FP16 m16n8k16 MMAs (half the MMA count of TF32 m16n8k8 for the same 11-bit
+// operand precision): Q, K, V, dO are scaled by per-CTA powers of two (largest row norm -> <= 1) and rounded to
+// FP16; P = exp(s - lse) <= 1 and dS' = P (dP' - D') = O(1) fit FP16 as they are. The power-of-two scales are
+// undone exactly by the output constants.
+//   phase A (16-row query blocks x 16-key steps): S = Q K^T, dP = dO V^T, dS, dQ += dS K
+//   phase B (16-row key blocks x 16-query steps): S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
+// P is recomputed from the saved log-sum-exp; the row constants (-lse, -D) enter as the accumulator start values.
+// Shared-memory operand images:
+//   row images  Xh[row][8 words]   word 2t = dims (2t, 2t+1), word 2t+1 = dims (2t+8, 2t+9): the B fragment pair of
+//                                  an 8-row tile is one LDS.64; A fragments take four scalar loads per row block
+//   transposed  Xt[dim][TS words]  16-row group m at words 8m.., word 8m + 2t (+1) = rows (2t, 2t+1) (+8) packed:
+//                                  the B fragment pair for a contraction over rows is one LDS.64
+constexpr int BWD_WARPS = 5;   // 160 threads: one row per thread at the reference's 151 tokens, two row blocks per warp
+constexpr int BWD_THREADS = BWD_WARPS * 32;
+__host__ __device__ inline int ts_stride(int Lr) {   // words per dim row of a transposed image, = 8 or 24 mod 32
+  int n = Lr / 2;
+  while (n % 32 != 8 && n % 32 != 24) n += 8;
+  return n;
+}
+__device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ float vldf(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
+// A fragment quad of rows (ra, ra + 8) from a row image. Scalar volatile loads: each value is its own register, so
+// the quad is allocated once as four consecutive registers (vector loads make ptxas re-shuffle them at every MMA).
+__device__ __forceinline__ void a_quad(const uint32_t* img, int ra, int t, uint32_t (&a)[4]) {
+  a[0] = vld(img + ra * 8 + 2 * t);
+  a[1] = vld(img + (ra + 8) * 8 + 2 * t);
+  a[2] = vld(img + ra * 8 + 2 * t + 1);
+  a[3] = vld(img + (ra + 8) * 8 + 2 * t + 1);
+}
+__device__ __forceinline__ void mma_f16_acc(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct BwdSmem {
+  uint32_t *Qh, *Kh, *Vh, *Gh;   // row images
+  uint32_t *Qt, *Kt, *Gt;        // transposed images
+  float *Ms, *Lm, *Dm;           // [Lr] additive key mask; -lse2 / cS; -D'
+  float4 *Lq, *Dq;               // [Lr / 8][4] the same two row constants as ready-made accumulator quads per (tile, t)
+  int* lidx;                     // live 16-key groups
+  int TS;
+};
+struct BwdScales {
+  float cS;   // score accumulator -> log2 units
+  float cQ, cK, cV;
+};
+
+// phase A for RB query blocks (rows r0 + rstride b) of one warp
+template <int RB>
+__device__ __forceinline__ void bwd_phase_a(int r0, int rstride, int L, int hg, int g, int t, const BwdSmem& S,
+                                            int nlive, const BwdScales& sc, float* __restrict__ dbase) {
+  uint32_t qa[RB][4], ga[RB][4];
+  float cs[RB][4], cd[RB][4];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+    const int ra = r0 + rstride * b + g;
+    a_quad(S.Qh, ra, t, qa[b]);
+    a_quad(S.Gh, ra, t, ga[b]);
+    cs[b][0] = vldf(S.Lm + ra), cs[b][1] = vldf(S.Lm + ra), cs[b][2] = vldf(S.Lm + ra + 8), cs[b][3] = vldf(S.Lm + ra + 8);
+    cd[b][0] = vldf(S.Dm + ra), cd[b][1] = vldf(S.Dm + ra), cd[b][2] = vldf(S.Dm + ra + 8), cd[b][3] = vldf(S.Dm + ra + 8);
+  }
+  float dq[RB][2][4];
+#pragma unroll
+  for (int b = 0; b < RB; ++b)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dq[b][0][i] = dq[b][1][i] = 0.f;
+  const uint32_t* kh = S.Kh + g * 8 + 2 * t;
+  const uint32_t* vh = S.Vh + g * 8 + 2 * t;
+  const uint32_t* kt = S.Kt + g * S.TS + 2 * t;
+  const float* ms = S.Ms + 2 * t;
+  for (int li = 0; li < nlive; ++li) {   // live key groups only (masked keys: P == 0 exactly)
+    const int m = S.lidx[li];
+    const uint2 kb0 = *reinterpret_cast<const uint2*>(kh + m * 128), kb1 = *reinterpret_cast<const uint2*>(kh + m * 128 + 64);
+    const uint2 vb0 = *reinterpret_cast<const uint2*>(vh + m * 128), vb1 = *reinterpret_cast<const uint2*>(vh + m * 128 + 64);
+    const float2 mk0 = *reinterpret_cast<const float2*>(ms + m * 16), mk1 = *reinterpret_cast<const float2*>(ms + m * 16 + 8);
+    const uint2 kt0 = *reinterpret_cast<const uint2*>(kt + m * 8), kt1 = *reinterpret_cast<const uint2*>(kt + 8 * S.TS + m * 8);
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      float s0[4], s1[4], p0[4], p1[4];
+      mma_f16(s0, qa[b][0], qa[b][1], qa[b][2], qa[b][3], kb0.x, kb0.y, cs[b][0], cs[b][1], cs[b][2], cs[b][3]);
+      mma_f16(s1, qa[b][0], qa[b][1], qa[b][2], qa[b][3], kb1.x, kb1.y, cs[b][0], cs[b][1], cs[b][2], cs[b][3]);
+      mma_f16(p0, ga[b][0], ga[b][1], ga[b][2], ga[b][3], vb0.x, vb0.y, cd[b][0], cd[b][1], cd[b][2], cd[b][3]);
+      mma_f16(p1, ga[b][0], ga[b][1], ga[b][2], ga[b][3], vb1.x, vb1.y, cd[b][0], cd[b][1], cd[b][2], cd[b][3]);
+      // dS' as the A operand of the contraction over the 16 keys: C layout of the two 8-key tiles == A layout
+      uint32_t a[4];
+      a[0] = pack_h2(ex2(fmaf(s0[0], sc.cS, mk0.x)) * p0[0], ex2(fmaf(s0[1], sc.cS, mk0.y)) * p0[1]);
+      a[1] = pack_h2(ex2(fmaf(s0[2], sc.cS, mk0.x)) * p0[2], ex2(fmaf(s0[3], sc.cS, mk0.y)) * p0[3]);
+      a[2] = pack_h2(ex2(fmaf(s1[0], sc.cS, mk1.x)) * p1[0], ex2(fmaf(s1[1], sc.cS, mk1.y)) * p1[1]);
+      a[3] = pack_h2(ex2(fmaf(s1[2], sc.cS, mk1.x)) * p1[2], ex2(fmaf(s1[3], sc.cS, mk1.y)) * p1[3]);
+      mma_f16_acc(dq[b][0], a, kt0.x, kt0.y);
+      mma_f16_acc(dq[b][1], a, kt1.x, kt1.y);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < RB; ++b)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = r0 + rstride * b + g + 8 * r;
+      if (row < L) {
+        float* dst = dbase + (size_t)row * 384 + hg + 2 * t;
+        *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dq[b][0][2 * r] * sc.cQ), tf32_rn(dq[b][0][2 * r + 1] * sc.cQ));
+        *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[b][1][2 * r] * sc.cQ), tf32_rn(dq[b][1][2 * r + 1] * sc.cQ));
+      }
+    }
+}
+
+// phase B for RB key blocks (rows j0 + rstride b) of one warp; tile rows are KEYS, columns are QUERIES
+template <int RB>
+__device__ __forceinline__ void bwd_phase_b(int j0, int rstride, int L, int Lr, int hg, int g, int t, const BwdSmem& S,
+                                            unsigned long long live_bits, const BwdScales& sc, float* __restrict__ dbase) {
+  uint32_t ka[RB][4], va[RB][4];
+  float ma[RB], mb[RB];
+  bool any_live = false;
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+    const int ja = j0 + rstride * b + g;
+    a_quad(S.Kh, ja, t, ka[b]);
+    a_quad(S.Vh, ja, t, va[b]);
+    ma[b] = S.Ms[ja], mb[b] = S.Ms[ja + 8];
+    const int grp = (j0 + rstride * b) >> 4;
+    any_live |= grp >= 64 || ((live_bits >> grp) & 1ull);
+  }
+  float dk[RB][2][4], dv[RB][2][4];
+#pragma unroll
+  for (int b = 0; b < RB; ++b)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dk[b][0][i] = dk[b][1][i] = dv[b][0][i] = dv[b][1][i] = 0.f;
+  const uint32_t* qh = S.Qh + g * 8 + 2 * t;
+  const uint32_t* gh = S.Gh + g * 8 + 2 * t;
+  const uint32_t* qt = S.Qt + g * S.TS + 2 * t;
+  const uint32_t* gt = S.Gt + g * S.TS + 2 * t;
+  // fully masked key blocks: dK = dV = 0 (still written below)
+  for (int m = 0; m < (any_live ? (Lr >> 4) : 0); ++m) {
+    const uint2 qb0 = *reinterpret_cast<const uint2*>(qh + m * 128), qb1 = *reinterpret_cast<const uint2*>(qh + m * 128 + 64);
+    const uint2 gb0 = *reinterpret_cast<const uint2*>(gh + m * 128), gb1 = *reinterpret_cast<const uint2*>(gh + m * 128 + 64);
+    const float4 l0 = S.Lq[(2 * m) * 4 + t], l1 = S.Lq[(2 * m + 1) * 4 + t];
+    const float4 d0 = S.Dq[(2 * m) * 4 + t], d1 = S.Dq[(2 * m + 1) * 4 + t];
+    const uint2 qt0 = *reinterpret_cast<const uint2*>(qt + m * 8), qt1 = *reinterpret_cast<const uint2*>(qt + 8 * S.TS + m * 8);
+    const uint2 gt0 = *reinterpret_cast<const uint2*>(gt + m * 8), gt1 = *reinterpret_cast<const uint2*>(gt + 8 * S.TS + m * 8);
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      float s0[4], s1[4], p0[4], p1[4];
+      mma_f16(s0, ka[b][0], ka[b][1], ka[b][2], ka[b][3], qb0.x, qb0.y, l0.x, l0.y, l0.z, l0.w);
+      mma_f16(s1, ka[b][0], ka[b][1], ka[b][2], ka[b][3], qb1.x, qb1.y, l1.x, l1.y, l1.z, l1.w);
+      mma_f16(p0, va[b][0], va[b][1], va[b][2], va[b][3], gb0.x, gb0.y, d0.x, d0.y, d0.z, d0.w);
+      mma_f16(p1, va[b][0], va[b][1], va[b][2], va[b][3], gb1.x, gb1.y, d1.x, d1.y, d1.z, d1.w);
+      const float e00 = ex2(fmaf(s0[0], sc.cS, ma[b])), e01 = ex2(fmaf(s0[1], sc.cS, ma[b]));
+      const float e02 = ex2(fmaf(s0[2], sc.cS, mb[b])), e03 = ex2(fmaf(s0[3], sc.cS, mb[b]));
+      const float e10 = ex2(fmaf(s1[0], sc.cS, ma[b])), e11 = ex2(fmaf(s1[1], sc.cS, ma[b]));
+      const float e12 = ex2(fmaf(s1[2], sc.cS, mb[b])), e13 = ex2(fmaf(s1[3], sc.cS, mb[b]));
+      uint32_t pa[4], sa[4];
+      pa[0] = pack_h2(e00, e01), pa[1] = pack_h2(e02, e03), pa[2] = pack_h2(e10, e11), pa[3] = pack_h2(e12, e13);
+      sa[0] = pack_h2(e00 * p0[0], e01 * p0[1]), sa[1] = pack_h2(e02 * p0[2], e03 * p0[3]);
+      sa[2] = pack_h2(e10 * p1[0], e11 * p1[1]), sa[3] = pack_h2(e12 * p1[2], e13 * p1[3]);
+      mma_f16_acc(dv[b][0], pa, gt0.x, gt0.y);
+      mma_f16_acc(dv[b][1], pa, gt1.x, gt1.y);
+      mma_f16_acc(dk[b][0], sa, qt0.x, qt0.y);
+      mma_f16_acc(dk[b][1], sa, qt1.x, qt1.y);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < RB; ++b)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = j0 + rstride * b + g + 8 * r;
+      if (row < L) {
+        float* dst = dbase + (size_t)row * 384 + 128 + hg + 2 * t;
+        *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[b][0][2 * r] * sc.cK), tf32_rn(dk[b][0][2 * r + 1] * sc.cK));
+        *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[b][1][2 * r] * sc.cK), tf32_rn(dk[b][1][2 * r + 1] * sc.cK));
+        *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[b][0][2 * r] * sc.cV), tf32_rn(dv[b][0][2 * r + 1] * sc.cV));
+        *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[b][1][2 * r] * sc.cV), tf32_rn(dv[b][1][2 * r + 1] * sc.cV));
+      }
+    }
+}
+
+// Staging: 4 lanes share a row (16 B = 4 dims each), so a warp-wide 16 B load covers 8 rows x 64 B: every sector
+// it touches is used in full. One chunk = 4 passes of 40 rows x the five matrices = 20 loads in flight per thread.
+constexpr int BWD_RPP = BWD_THREADS / 4;   // rows per pass
+struct BwdChunk {
+  float4 q[4], k[4], v[4], g[4], o[4];
+  float lse[4];
+};
+__device__ __forceinline__ void bwd_load_chunk(const float* __restrict__ base, const float* __restrict__ obase,
+                                               const float* __restrict__ dobase, const float* __restrict__ lse_c, int row0,
+                                               int L, int hg, int h, BwdChunk& d) {
+  const int sub = threadIdx.x & 3, rloc = threadIdx.x >> 2;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int r = row0 + rloc + BWD_RPP * p;
+    const bool ok = r < L;
+    const int rr = min(r, L - 1);
+    const float* qp = base + (size_t)rr * 384 + hg + sub * 4;
+    d.q[p] = ok ? *reinterpret_cast<const float4*>(qp) : z;
+    d.k[p] = ok ? *reinterpret_cast<const float4*>(qp + 128) : z;
+    d.v[p] = ok ? *reinterpret_cast<const float4*>(qp + 256) : z;
+    d.g[p] = ok ? *reinterpret_cast<const float4*>(dobase + (size_t)rr * 128 + hg + sub * 4) : z;
+    d.o[p] = ok ? *reinterpret_cast<const float4*>(obase + (size_t)rr * 128 + hg + sub * 4) : z;
+    d.lse[p] = (ok && sub == 0) ? lse_c[(size_t)rr * 8 + h] : INFINITY;   // padded queries: 2^(score - inf) == 0
+  }
+}
+__device__ __forceinline__ float quad_sum(float x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  return x;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+// FP16 row image + transposed image of the 4 dims a lane holds of row r; every lane of the warp calls this (rows
+// 2i and 2i + 1 meet by shuffle: they share the words of the transposed image)
+__device__ __forceinline__ void bwd_store_images(const float4& v, float scale, int r, int Lr, uint32_t* rowimg,
+                                                 uint32_t* timg, int TS) {
+  const int sub = threadIdx.x & 3;
+  const float x0 = v.x * scale, x1 = v.y * scale, x2 = v.z * scale, x3 = v.w * scale;
+  const bool act = r < Lr;
+  if (act) {
+    uint32_t* w = rowimg + r * 8 + (sub < 2 ? 4 * sub : 4 * (sub - 2) + 1);
+    w[0] = pack_h2(x0, x1);
+    w[2] = pack_h2(x2, x3);
+  }
+  if (timg) {
+    const int odd = r & 1;
+    const float o0 = __shfl_xor_sync(0xffffffffu, odd ? x0 : x2, 4), o1 = __shfl_xor_sync(0xffffffffu, odd ? x1 : x3, 4);
+    if (act) {
+      uint32_t* w = timg + (4 * sub + 2 * odd) * TS + 8 * (r >> 4) + 2 * ((r & 7) >> 1) + ((r & 15) >> 3);
+      w[0] = odd ? pack_h2(o0, x2) : pack_h2(x0, o0);
+      w[TS] = odd ? pack_h2(o1, x3) : pack_h2(x1, o1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 3) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
+                                                                   const float* __restrict__ lse, const float* __restrict__ datt,
+                                                                   const float* __restrict__ mask, int mS, int m0, int L,
+                                                                   int pf_dist, float* __restrict__ dqkv) {
   extern __shared__ float sm[];
-  const int ntiles = (L + 7) >> 3;
-  const int Lp = ntiles * 8;
-  const int Lr = (Lp + 15) & ~15;    // rows staged (A fragments read 16-row blocks)
-  float* Qs = sm;
-  float* Ks = Qs + Lr * KS;
-  float* Vs = Ks + Lr * KS;
-  float* Gs = Vs + Lr * KS;          // dO
-  float* Ms = Gs + Lr * KS;          // [Lr] additive key mask
-  float* Ls = Ms + Lr;               // [Lr] log-sum-exp (log2 units), +inf on padding
-  float* Ds = Ls + Lr;               // [Lr]
-  int* live = reinterpret_cast<int*>(Ds + Lr);   // [ntiles]
-  int* lidx = live + ntiles;                     // [ntiles] compact list of live tiles
+  __shared__ unsigned nrm_bits[4];          // largest squared row norm of Q, K, V, dO
+  __shared__ unsigned long long live_bits_s;
+  __shared__ int n_live_s;
+  const int Lr = (L + 15) & ~15, ngrp = Lr >> 4;
+  BwdSmem S;
+  S.TS = ts_stride(Lr);
+  S.Qh = reinterpret_cast<uint32_t*>(sm);
+  S.Kh = S.Qh + Lr * 8;
+  S.Vh = S.Kh + Lr * 8;
+  S.Gh = S.Vh + Lr * 8;
+  S.Qt = S.Gh + Lr * 8;
+  S.Kt = S.Qt + 16 * S.TS;
+  S.Gt = S.Kt + 16 * S.TS;
+  S.Lq = reinterpret_cast<float4*>(S.Gt + 16 * S.TS);
+  S.Dq = S.Lq + (Lr >> 3) * 4;
+  S.Ms = reinterpret_cast<float*>(S.Dq + (Lr >> 3) * 4);
+  S.Lm = S.Ms + Lr;
+  S.Dm = S.Lm + Lr;
+  S.lidx = reinterpret_cast<int*>(S.Dm + Lr);
   // heads are the fastest-varying block index: the 8 CTAs of a state run side by side and share the 128-byte
   // lines / DRAM pages of its rows (a head only touches 64 B of each 1536 B qkv row)
-  const int c = blockIdx.x >> 3, h = blockIdx.x & 7;
+  const int c = blockIdx.x >> 3, h = blockIdx.x & 7, hg = h * 16;
   const float* base = qkv + (size_t)c * L * 384;
   const float* obase = att + (size_t)c * L * 128;
   const float* dobase = datt + (size_t)c * L * 128;
+  const float* lse_c = lse + (size_t)c * L * 8;
   float* dbase = dqkv + (size_t)c * L * 384;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int hg = h * 16;
-
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const bool single = Lr <= 4 * BWD_RPP;   // one chunk: the rows wait in registers for the scales
   ATTN_STAMP(0);
-  stage_async(base, 384, hg, L, Lr, Qs);
-  stage_async(base, 384, 128 + hg, L, Lr, Ks);
-  stage_async(base, 384, 256 + hg, L, Lr, Vs);
-  stage_async(dobase, 128, hg, L, Lr, Gs);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int j = threadIdx.x; j < Lr; j += blockDim.x)
-    Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
-  for (int i = threadIdx.x; i < Lr; i += blockDim.x) {
-    float d = 0.f, l = INFINITY;   // padded queries: 2^(score - inf) == 0
-    if (i < L) {
-      const float4* op = reinterpret_cast<const float4*>(obase + (size_t)i * 128 + hg);
-      const float4* dp = reinterpret_cast<const float4*>(dobase + (size_t)i * 128 + hg);
-      float4 a[4], b[4];
+  BwdChunk d;
+  float nq = 0.f, nk = 0.f, nv = 0.f, ng = 0.f;
+  if (single) bwd_load_chunk(base, obase, dobase, lse_c, 0, L, hg, h, d);
+  if (tid < 4) nrm_bits[tid] = 0u;
+  for (int j = tid; j < Lr; j += BWD_THREADS) S.Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
+  for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
+    if (!single) bwd_load_chunk(base, obase, dobase, lse_c, row0, L, hg, h, d);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = op[q]; b[q] = dp[q]; }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        d = fmaf(a[q].x, b[q].x, d); d = fmaf(a[q].y, b[q].y, d); d = fmaf(a[q].z, b[q].z, d); d = fmaf(a[q].w, b[q].w, d);
-      }
-      l = lse[((size_t)c * L + i) * 8 + h] * LOG2E;
+    for (int p = 0; p < 4; ++p) {
+      nq = fmaxf(nq, dot4(d.q[p], d.q[p])), nk = fmaxf(nk, dot4(d.k[p], d.k[p]));
+      nv = fmaxf(nv, dot4(d.v[p], d.v[p])), ng = fmaxf(ng, dot4(d.g[p], d.g[p]));
     }
-    Ds[i] = d;
-    Ls[i] = l;
   }
+  // (per-lane maxima of quarter-row sums of squares: 4 x the largest is an upper bound of the largest row norm^2)
+  nq = 4.f * __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(nq)));
+  nk = 4.f * __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(nk)));
+  nv = 4.f * __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(nv)));
+  ng = 4.f * __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ng)));
+  __syncthreads();   // nrm_bits zeroed, Ms written
+  if (lane == 0) {
+    atomicMax(&nrm_bits[0], __float_as_uint(nq));
+    atomicMax(&nrm_bits[1], __float_as_uint(nk));
+    atomicMax(&nrm_bits[2], __float_as_uint(nv));
+    atomicMax(&nrm_bits[3], __float_as_uint(ng));
+  }
+  if (warp == 0) {
+    // ordered list + bit mask of the live 16-key groups (see build_live_list for the exactness argument)
+    int n = 0;
+    unsigned long long bits = 0ull;
+    for (int m0_ = 0; m0_ < ngrp; m0_ += 32) {
+      const int m = m0_ + lane;
+      bool l = false;
+      if (m < ngrp)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(S.Ms + m * 16 + q * 4);
+          l = l || x.x == 0.f || x.y == 0.f || x.z == 0.f || x.w == 0.f;
+        }
+      const unsigned bal = __ballot_sync(0xffffffffu, l);
+      if (l) S.lidx[n + __popc(bal & ((1u << lane) - 1u))] = m;
+      n += __popc(bal);
+      if (m0_ < 64) bits |= (unsigned long long)bal << m0_;
+    }
+    if (n == 0) {
+      for (int m = lane; m < ngrp; m += 32) S.lidx[m] = m;
+      n = ngrp;
+      bits = ~0ull;
+    }
+    if (lane == 0) n_live_s = n, live_bits_s = bits;
+  }
+  __syncthreads();
   ATTN_STAMP(1);
+  float q_dn, q_up, k_dn, k_up, v_dn, v_up, g_dn, g_up;
+  // Q, K only feed fp32 accumulators: use FP16's range. dS' = P (dO' V'^T - D') is itself an FP16 operand and is
+  // bounded by 2 |dO'| |V'| <= 2^15.
+  pow2_scale(__uint_as_float(nrm_bits[0]), 14, q_dn, q_up);
+  pow2_scale(__uint_as_float(nrm_bits[1]), 14, k_dn, k_up);
+  pow2_scale(__uint_as_float(nrm_bits[2]), 7, v_dn, v_up);
+  pow2_scale(__uint_as_float(nrm_bits[3]), 7, g_dn, g_up);
+  BwdScales sc;
+  sc.cS = QSCALE * q_up * k_up;
+  sc.cQ = 0.25f * g_up * v_up * k_up;
+  sc.cK = 0.25f * g_up * v_up * q_up;
+  sc.cV = g_up;
+  const float inv_cS = 1.f / sc.cS, d_scale = g_dn * v_dn;
+  for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
+    if (!single) bwd_load_chunk(base, obase, dobase, lse_c, row0, L, hg, h, d);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int r = row0 + (tid >> 2) + BWD_RPP * p;
+      bwd_store_images(d.q[p], q_dn, r, Lr, S.Qh, S.Qt, S.TS);
+      bwd_store_images(d.k[p], k_dn, r, Lr, S.Kh, S.Kt, S.TS);
+      bwd_store_images(d.v[p], v_dn, r, Lr, S.Vh, nullptr, S.TS);
+      bwd_store_images(d.g[p], g_dn, r, Lr, S.Gh, S.Gt, S.TS);
+      const float dd = quad_sum(dot4(d.g[p], d.o[p]));   // D = sum_d dO O of the row
+      if (r < Lr && (tid & 3) == 0) {
+        const float lm = -(d.lse[p] * LOG2E) * inv_cS, dm = -dd * d_scale;
+        S.Lm[r] = lm;
+        S.Dm[r] = dm;
+        // accumulator quads of phase B: column (query) r sits at positions (r & 1) and (r & 1) + 2 of quad [r / 8][(r & 7) / 2]
+        float* lq = reinterpret_cast<float*>(S.Lq + (r >> 3) * 4 + ((r & 7) >> 1)) + (r & 1);
+        float* dq = reinterpret_cast<float*>(S.Dq + (r >> 3) * 4 + ((r & 7) >> 1)) + (r & 1);
+        lq[0] = lm, lq[2] = lm;
+        dq[0] = dm, dq[2] = dm;
+      }
+    }
+  }
   __syncthreads();
-  mark_live_tiles(Ms, live, ntiles);   // the mask bookkeeping runs while the copies are in flight
-  __syncthreads();
-  LiveBits lbits;
-  lbits.load(live, ntiles);
-  const int nlive = compact_live(live, lidx, ntiles);
   ATTN_STAMP(2);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  // pull the rows of the item one wave of CTAs ahead into L2 while this one computes
+  {
+    const int nxt = blockIdx.x + pf_dist;
+    if (nxt < (int)gridDim.x) {
+      const int c2 = nxt >> 3, hg2 = (nxt & 7) * 16;
+      const float* b2 = qkv + (size_t)c2 * L * 384 + hg2;
+      const float* o2 = att + (size_t)c2 * L * 128 + hg2;
+      const float* g2 = datt + (size_t)c2 * L * 128 + hg2;
+      for (int r = tid; r < L; r += BWD_THREADS) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)r * 384));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)r * 384 + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)r * 384 + 256));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(o2 + (size_t)r * 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(g2 + (size_t)r * 128));
+      }
+    }
+  }
+  const int nlive = n_live_s;
+  const unsigned long long live_bits = live_bits_s;
+  // Warp w always runs on SM sub-partition w % 4: rotate the block assignment per CTA so the sub-partitions stay
+  // evenly loaded when the block count is not a multiple of the warp count.
+  const int rot = ((warp + ((blockIdx.x * 0x9E3779B1u) >> 29)) % BWD_WARPS) * 16, stride = BWD_WARPS * 16;
+  {
+    int r0 = rot;
+    for (; r0 + stride < L; r0 += 2 * stride) bwd_phase_a<2>(r0, stride, L, hg, g, t, S, nlive, sc, dbase);
+    if (r0 < L) bwd_phase_a<1>(r0, stride, L, hg, g, t, S, nlive, sc, dbase);
+  }
   ATTN_STAMP(3);
-
-  // ---------------- phase A: dQ = dS K / 4 ----------------
-  for (int r0 = warp * 16; r0 < L; r0 += 64) {
-    uint32_t qa[2][4], da[2][4];
-    lds_a_frag(Qs, r0 + g, r0 + g + 8, 0, t, QSCALE, qa[0]);
-    lds_a_frag(Qs, r0 + g, r0 + g + 8, 8, t, QSCALE, qa[1]);
-    lds_a_frag(Gs, r0 + g, r0 + g + 8, 0, t, 1.f, da[0]);
-    lds_a_frag(Gs, r0 + g, r0 + g + 8, 8, t, 1.f, da[1]);
-    const float la = Ls[r0 + g], lb = Ls[r0 + g + 8];
-    const float Da = Ds[r0 + g], Db = Ds[r0 + g + 8];
-    float dq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 2
-    for (int li = 0; li < nlive; ++li) {   // live key tiles only (masked keys: P == 0 exactly)
-      const int nt = lidx[li];
-      float s[4] = {-la, -la, -lb, -lb}, dp[4] = {-Da, -Da, -Db, -Db};
-      const float* kr = Ks + (nt * 8 + g) * KS + t;
-      const float* vr = Vs + (nt * 8 + g) * KS + t;
-      mma_tf32(s, qa[0][0], qa[0][1], qa[0][2], qa[0][3], tfbits(kr[0]), tfbits(kr[4]));
-      mma_tf32(s, qa[1][0], qa[1][1], qa[1][2], qa[1][3], tfbits(kr[8]), tfbits(kr[12]));
-      mma_tf32(dp, da[0][0], da[0][1], da[0][2], da[0][3], tfbits(vr[0]), tfbits(vr[4]));
-      mma_tf32(dp, da[1][0], da[1][1], da[1][2], da[1][3], tfbits(vr[8]), tfbits(vr[12]));
-      const float2 mk = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
-      const float p0 = ex2(s[0] + mk.x), p1 = ex2(s[1] + mk.y);
-      const float p2 = ex2(s[2] + mk.x), p3 = ex2(s[3] + mk.y);
-      // dS as A operand (k relabelled: t <-> key 2t, t+4 <-> key 2t+1)
-      const uint32_t a0 = tfbits(p0 * dp[0]), a2 = tfbits(p1 * dp[1]);
-      const uint32_t a1 = tfbits(p2 * dp[2]), a3 = tfbits(p3 * dp[3]);
-      const float* k0 = Ks + (nt * 8 + 2 * t) * KS + g;
-      mma_tf32(dq[0], a0, a1, a2, a3, tfbits(k0[0]), tfbits(k0[KS]));
-      mma_tf32(dq[1], a0, a1, a2, a3, tfbits(k0[8]), tfbits(k0[KS + 8]));
-    }
-    const int ra = r0 + g, rb = r0 + g + 8;
-    if (ra < L) {
-      float* dst = dbase + (size_t)ra * 384 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dq[0][0] * 0.25f), tf32_rn(dq[0][1] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[1][0] * 0.25f), tf32_rn(dq[1][1] * 0.25f));
-    }
-    if (rb < L) {
-      float* dst = dbase + (size_t)rb * 384 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dq[0][2] * 0.25f), tf32_rn(dq[0][3] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dq[1][2] * 0.25f), tf32_rn(dq[1][3] * 0.25f));
-    }
+  {
+    int j0 = rot;
+    for (; j0 + stride < L; j0 += 2 * stride) bwd_phase_b<2>(j0, stride, L, Lr, hg, g, t, S, live_bits, sc, dbase);
+    if (j0 < L) bwd_phase_b<1>(j0, stride, L, Lr, hg, g, t, S, live_bits, sc, dbase);
   }
-
   ATTN_STAMP(4);
-  // ---------------- phase B: dK = dS^T Q / 4, dV = P^T dO (tile rows are KEYS, columns are QUERIES) ----------------
-  for (int j0 = warp * 16; j0 < L; j0 += 64) {
-    uint32_t ka[2][4], va[2][4];
-    lds_a_frag(Ks, j0 + g, j0 + g + 8, 0, t, QSCALE, ka[0]);
-    lds_a_frag(Ks, j0 + g, j0 + g + 8, 8, t, QSCALE, ka[1]);
-    lds_a_frag(Vs, j0 + g, j0 + g + 8, 0, t, 1.f, va[0]);
-    lds_a_frag(Vs, j0 + g, j0 + g + 8, 8, t, 1.f, va[1]);
-    const int ja = j0 + g, jb = j0 + g + 8;
-    const float ma = Ms[ja], mb = Ms[jb];
-    float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    // both 8-key tiles of this block masked: dK = dV = 0 (still written below)
-    const bool dead = !lbits.test(j0 >> 3) && !(((j0 >> 3) + 1 < ntiles) && lbits.test((j0 >> 3) + 1));
-#pragma unroll 2
-    for (int it = 0; it < (dead ? 0 : ntiles); ++it) {
-      const float2 l01 = *reinterpret_cast<const float2*>(Ls + it * 8 + 2 * t);   // query columns 2t, 2t+1
-      const float2 D01 = *reinterpret_cast<const float2*>(Ds + it * 8 + 2 * t);
-      float s[4] = {-l01.x, -l01.y, -l01.x, -l01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
-      const float* qr = Qs + (it * 8 + g) * KS + t;
-      const float* dr = Gs + (it * 8 + g) * KS + t;
-      mma_tf32(s, ka[0][0], ka[0][1], ka[0][2], ka[0][3], tfbits(qr[0]), tfbits(qr[4]));
-      mma_tf32(s, ka[1][0], ka[1][1], ka[1][2], ka[1][3], tfbits(qr[8]), tfbits(qr[12]));
-      mma_tf32(dp, va[0][0], va[0][1], va[0][2], va[0][3], tfbits(dr[0]), tfbits(dr[4]));
-      mma_tf32(dp, va[1][0], va[1][1], va[1][2], va[1][3], tfbits(dr[8]), tfbits(dr[12]));
-      const float p0 = ex2(s[0] + ma), p1 = ex2(s[1] + ma);
-      const float p2 = ex2(s[2] + mb), p3 = ex2(s[3] + mb);
-      const uint32_t pa0 = tfbits(p0), pa2 = tfbits(p1), pa1 = tfbits(p2), pa3 = tfbits(p3);
-      const uint32_t sa0 = tfbits(p0 * dp[0]), sa2 = tfbits(p1 * dp[1]);
-      const uint32_t sa1 = tfbits(p2 * dp[2]), sa3 = tfbits(p3 * dp[3]);
-      const float* d0 = Gs + (it * 8 + 2 * t) * KS + g;
-      const float* q0 = Qs + (it * 8 + 2 * t) * KS + g;
-      mma_tf32(dv[0], pa0, pa1, pa2, pa3, tfbits(d0[0]), tfbits(d0[KS]));
-      mma_tf32(dv[1], pa0, pa1, pa2, pa3, tfbits(d0[8]), tfbits(d0[KS + 8]));
-      mma_tf32(dk[0], sa0, sa1, sa2, sa3, tfbits(q0[0]), tfbits(q0[KS]));
-      mma_tf32(dk[1], sa0, sa1, sa2, sa3, tfbits(q0[8]), tfbits(q0[KS + 8]));
-    }
-    if (ja < L) {
-      float* dst = dbase + (size_t)ja * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][0] * 0.25f), tf32_rn(dk[0][1] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][0] * 0.25f), tf32_rn(dk[1][1] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][0]), tf32_rn(dv[0][1]));
-      *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][0]), tf32_rn(dv[1][1]));
-    }
-    if (jb < L) {
-      float* dst = dbase + (size_t)jb * 384 + 128 + hg + 2 * t;
-      *reinterpret_cast<float2*>(dst) = make_float2(tf32_rn(dk[0][2] * 0.25f), tf32_rn(dk[0][3] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 8) = make_float2(tf32_rn(dk[1][2] * 0.25f), tf32_rn(dk[1][3] * 0.25f));
-      *reinterpret_cast<float2*>(dst + 128) = make_float2(tf32_rn(dv[0][2]), tf32_rn(dv[0][3]));
-      *reinterpret_cast<float2*>(dst + 136) = make_float2(tf32_rn(dv[1][2]), tf32_rn(dv[1][3]));
-    }
-  }
-  ATTN_STAMP(5);
-  __syncthreads();
-  ATTN_STAMP(6);
 }
 
 }  // namespace
@@ -687,16 +837,22 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
 int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
                   int m0, int C, int L, float* dqkv, cudaStream_t st) {
   if (C <= 0) return TPC_OK;
-  if (L < 1 || L > 1024) return TPC_ERR_SHAPE;
-  const int Lp = ((L + 7) / 8) * 8;
-  const int Lr = (Lp + 15) & ~15;
-  const size_t smem = (size_t)(4 * Lr * KS + 3 * Lr + 2 * (Lp / 8) + 8) * sizeof(float);
+  if (L < 1 || L > 512) return TPC_ERR_SHAPE;
+  const int Lr = (L + 15) & ~15;
+  const size_t smem = (size_t)(4 * Lr * 8 + 3 * 16 * ts_stride(Lr) + 2 * (Lr / 8) * 16 + 3 * Lr + Lr / 16 + 8) * sizeof(float);
   static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static int resident = 0;   // CTAs in flight on the whole GPU = the L2 prefetch distance
+  if (smem > attr_smem || resident == 0) {
     TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
+    int dev = 0, sms = 0, per_sm = 0;
+    TPC_CHECK_CUDA(cudaGetDevice(&dev));
+    TPC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_bwd_kernel, BWD_THREADS, smem));
+    if (per_sm < 1) return TPC_ERR_SHAPE;
+    resident = sms * per_sm;
   }
-  attn_bwd_kernel<<<C * 8, 128, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, dqkv);
+  attn_bwd_kernel<<<C * 8, BWD_THREADS, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, resident, dqkv);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
