@@ -270,8 +270,6 @@ __device__ __forceinline__ void fwd_row_blocks(int r0, int rstride, int L, int h
   }
 }
 
-constexpr int FWD_WARPS = 4;
-constexpr int FWD_THREADS = FWD_WARPS * 32;
 constexpr int RS = 20;   // raw (cp.async) row stride in floats: 16 of one head + 4, conflict-free float4 row reads
 
 // cp.async of the head's 16 columns of rows [0, L) of matrix m (Q, K, V = column blocks 0, 1, 2 of qkv) into raw
@@ -302,10 +300,12 @@ __device__ __forceinline__ void raw_row(const float* raw, int r, int L, float4 (
 // (fp32-level logits: the softmax amplifies score errors); P.V is plain TF32 with P, V rounded to nearest (3xTF32
 // below 64 tokens, where there is no averaging of the rounding). The row maximum is only searched (pass 1) when
 // the norm bound says the exponentials could leave fp32 range.
-template <bool PV3X>
-__global__ void __launch_bounds__(FWD_THREADS, 3) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+// NW warps per CTA: 2 up to 64 tokens (each warp two row blocks; twice the CTAs in flight), else 4.
+template <bool PV3X, int NW>
+__global__ void __launch_bounds__(NW * 32, 12 / NW) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                           int mS, int m0, int L, int nitems, float* __restrict__ att,
                                                           float* __restrict__ lse) {
+  constexpr int FWD_WARPS = NW, FWD_THREADS = NW * 32;
   extern __shared__ float sm[];
   __shared__ unsigned nrm_bits[2][2];   // [item parity][Q, K]: largest squared row norm (non-negative floats order as uints)
   __shared__ int n_live_s;
@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) attn_fwd_kernel(const float* _
 //                                  an 8-row tile is one LDS.64; A fragments take four scalar loads per row block
 //   transposed  Xt[dim][TS words]  16-row group m at words 8m.., word 8m + 2t (+1) = rows (2t, 2t+1) (+8) packed:
 //                                  the B fragment pair for a contraction over rows is one LDS.64
-constexpr int BWD_WARPS = 5;   // 160 threads: one row per thread at the reference's 151 tokens, two row blocks per warp
-constexpr int BWD_THREADS = BWD_WARPS * 32;
+// The kernels are templated on the warp count NW = ceil(16-row blocks / 2), at most 5 (160 threads at the
+// reference's 151 tokens): every warp then owns two row blocks and the staging needs one chunk.
 __host__ __device__ inline int ts_stride(int Lr) {   // words per dim row of a transposed image, = 8 or 24 mod 32
   int n = Lr / 2;
   while (n % 32 != 8 && n % 32 != 24) n += 8;
@@ -589,11 +589,11 @@ __device__ __forceinline__ void bwd_phase_b(int j0, int rstride, int L, int Lr, 
 
 // Staging: 4 lanes share a row (16 B = 4 dims each), so a warp-wide 16 B load covers 8 rows x 64 B: every sector
 // it touches is used in full. One chunk = 4 passes of 40 rows x the five matrices = 20 loads in flight per thread.
-constexpr int BWD_RPP = BWD_THREADS / 4;   // rows per pass
 struct BwdChunk {
   float4 q[4], k[4], v[4], g[4], o[4];
   float lse[4];
 };
+template <int RPP>   // rows per pass = threads / 4
 __device__ __forceinline__ void bwd_load_chunk(const float* __restrict__ base, const float* __restrict__ obase,
                                                const float* __restrict__ dobase, const float* __restrict__ lse_c, int row0,
                                                int L, int hg, int h, BwdChunk& d) {
@@ -601,7 +601,7 @@ __device__ __forceinline__ void bwd_load_chunk(const float* __restrict__ base, c
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    const int r = row0 + rloc + BWD_RPP * p;
+    const int r = row0 + rloc + RPP * p;
     const bool ok = r < L;
     const int rr = min(r, L - 1);
     const float* qp = base + (size_t)rr * 384 + hg + sub * 4;
@@ -644,7 +644,8 @@ __device__ __forceinline__ void bwd_store_images(const float4& v, float scale, i
   }
 }
 
-__global__ void __launch_bounds__(BWD_THREADS, 3) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
                                                                    const float* __restrict__ lse, const float* __restrict__ datt,
                                                                    const float* __restrict__ mask, int mS, int m0, int L,
                                                                    int pf_dist, float* __restrict__ dqkv) {
@@ -677,15 +678,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) attn_bwd_kernel(const float* _
   const float* lse_c = lse + (size_t)c * L * 8;
   float* dbase = dqkv + (size_t)c * L * 384;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  constexpr int BWD_THREADS = NW * 32, BWD_WARPS = NW, BWD_RPP = NW * 8;
   const bool single = Lr <= 4 * BWD_RPP;   // one chunk: the rows wait in registers for the scales
   ATTN_STAMP(0);
   BwdChunk d;
   float nq = 0.f, nk = 0.f, nv = 0.f, ng = 0.f;
-  if (single) bwd_load_chunk(base, obase, dobase, lse_c, 0, L, hg, h, d);
+  if (single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, 0, L, hg, h, d);
   if (tid < 4) nrm_bits[tid] = 0u;
   for (int j = tid; j < Lr; j += BWD_THREADS) S.Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
   for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
-    if (!single) bwd_load_chunk(base, obase, dobase, lse_c, row0, L, hg, h, d);
+    if (!single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, row0, L, hg, h, d);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       nq = fmaxf(nq, dot4(d.q[p], d.q[p])), nk = fmaxf(nk, dot4(d.k[p], d.k[p]));
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) attn_bwd_kernel(const float* _
   sc.cV = g_up;
   const float inv_cS = 1.f / sc.cS, d_scale = g_dn * v_dn;
   for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
-    if (!single) bwd_load_chunk(base, obase, dobase, lse_c, row0, L, hg, h, d);
+    if (!single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, row0, L, hg, h, d);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int r = row0 + (tid >> 2) + BWD_RPP * p;
@@ -814,22 +816,22 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
   const size_t smem = (size_t)((Lr + Lp) * 16 + (L < 64 ? 32 : 16) * vt_stride(Lp) + Lp + ((nt + 3) & ~3) + 3 * Lp * RS + Lp) *
                       sizeof(float);
   // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
-  static size_t attr_smem[2] = {0, 0};
-  static int ctas_per_sm[2] = {0, 0}, num_sms = 0;
-  const int v = L < 64 ? 1 : 0;
-  auto kern = v ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  static size_t attr_smem[3] = {0, 0, 0};
+  static int ctas_per_sm[3] = {0, 0, 0}, num_sms = 0;
+  const int v = L < 64 ? 0 : (L == 64 ? 1 : 2), nw = v == 2 ? 4 : 2;
+  auto kern = v == 0 ? attn_fwd_kernel<true, 2> : (v == 1 ? attn_fwd_kernel<false, 2> : attn_fwd_kernel<false, 4>);
   if (smem > attr_smem[v] || ctas_per_sm[v] == 0) {
     TPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[v] = smem;
     int dev = 0;
     TPC_CHECK_CUDA(cudaGetDevice(&dev));
     TPC_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[v], kern, FWD_THREADS, smem));
+    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[v], kern, nw * 32, smem));
     if (ctas_per_sm[v] < 1) return TPC_ERR_SHAPE;
   }
   const int nitems = C * 8;
   const int grid = nitems < num_sms * ctas_per_sm[v] ? nitems : num_sms * ctas_per_sm[v];
-  kern<<<grid, FWD_THREADS, smem, st>>>(qkv, mask, mS, m0, L, nitems, att, lse);
+  kern<<<grid, nw * 32, smem, st>>>(qkv, mask, mS, m0, L, nitems, att, lse);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
@@ -840,19 +842,23 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
   if (L < 1 || L > 512) return TPC_ERR_SHAPE;
   const int Lr = (L + 15) & ~15;
   const size_t smem = (size_t)(4 * Lr * 8 + 3 * 16 * ts_stride(Lr) + 2 * (Lr / 8) * 16 + 3 * Lr + Lr / 16 + 8) * sizeof(float);
-  static size_t attr_smem = 0;
-  static int resident = 0;   // CTAs in flight on the whole GPU = the L2 prefetch distance
-  if (smem > attr_smem || resident == 0) {
-    TPC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  const int nblk = Lr / 16, nw = nblk >= 9 ? 5 : (nblk + 1) / 2, v = nw - 1;
+  using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, int, int, int, int, float*);
+  static const Kern kerns[5] = {attn_bwd_kernel<1>, attn_bwd_kernel<2>, attn_bwd_kernel<3>, attn_bwd_kernel<4>,
+                                attn_bwd_kernel<5>};
+  static size_t attr_smem[5] = {0, 0, 0, 0, 0};
+  static int resident[5] = {0, 0, 0, 0, 0};   // CTAs in flight on the whole GPU = the L2 prefetch distance
+  if (smem > attr_smem[v] || resident[v] == 0) {
+    TPC_CHECK_CUDA(cudaFuncSetAttribute(kerns[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[v] = smem;
     int dev = 0, sms = 0, per_sm = 0;
     TPC_CHECK_CUDA(cudaGetDevice(&dev));
     TPC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_bwd_kernel, BWD_THREADS, smem));
+    TPC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kerns[v], nw * 32, smem));
     if (per_sm < 1) return TPC_ERR_SHAPE;
-    resident = sms * per_sm;
+    resident[v] = sms * per_sm;
   }
-  attn_bwd_kernel<<<C * 8, BWD_THREADS, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, resident, dqkv);
+  kerns[v]<<<C * 8, nw * 32, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, resident[v], dqkv);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
