@@ -125,9 +125,8 @@ __device__ __forceinline__ float norm2(const float4 (&v)[4]) {
 // ordered list of the live 8-key tiles (a tile is live if it holds an unmasked key), built by one warp with ballots.
 // A masked key contributes exp(-1e9 - max) == 0 exactly in fp32, so dead tiles are skipped: exact, and
 // during an episode a third to a half of the keys (placed rules, full nodes) are masked. If nothing is unmasked
-// (cannot happen on the reference's trajectories) every tile stays live and the arithmetic degenerates to the
-// reference's uniform softmax over equal -1e9 logits.
-__device__ __forceinline__ void build_live_list(const float* Ms, int* lidx, int* n_out, int ntiles, int lane) {
+// (cannot happen on the reference's trajectories) every tile stays live and the softmax is uniform, as in the reference.
+__device__ __forceinline__ void build_live_list(float* Ms, int* lidx, int* n_out, int ntiles, int lane, float fill) {
   int n = 0;
   for (int nt0 = 0; nt0 < ntiles; nt0 += 32) {
     const int nt = nt0 + lane;
@@ -141,8 +140,13 @@ __device__ __forceinline__ void build_live_list(const float* Ms, int* lidx, int*
     n += __popc(bal);
   }
   if (n == 0) {
+    // nothing unmasked: in the reference's fp32 the scores vanish in the rounding of score + (-1e9) and the softmax is
+    // uniform over all keys. Same here: every tile live, the mask term dropped; the caller zeroes the score scale
+    // (n_out < 0 flags the case).
     for (int nt = lane; nt < ntiles; nt += 32) lidx[nt] = nt;
-    n = ntiles;
+    for (int j = lane; j < ntiles * 8; j += 32)
+      if (Ms[j] != -INFINITY) Ms[j] = fill;
+    n = -ntiles;
   }
   if (lane == 0) *n_out = n;
 }
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) attn_fwd_kernel(const float*
     ATTN_STAMP(2);
     __syncthreads();
     ATTN_STAMP(3);
-    if (warp == 0) build_live_list(Ms, lidx, &n_live_s, ntiles, lane);
+    if (warp == 0) build_live_list(Ms, lidx, &n_live_s, ntiles, lane, 0.f);
     if (tid < 2) nrm_bits[par ^ 1][tid] = 0u;   // for the next item (its atomics come after the next barrier)
     const float q2max = __uint_as_float(nrm_bits[par][0]), k2max = __uint_as_float(nrm_bits[par][1]);
     float q_down, q_up, k_down, k_up;
@@ -388,9 +392,11 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) attn_fwd_kernel(const float*
     __syncthreads();   // images ready; raw is free again
     if (item + (int)gridDim.x < nitems) prefetch(item + gridDim.x);
     ATTN_STAMP(5);
-    const int nlive = n_live_s;
-    const float sc_mul = QSCALE * q_up * k_up;                                  // accumulator -> log2-unit score
-    const bool easy = q2max * k2max * (QSCALE * QSCALE) < EASY_BOUND * EASY_BOUND;   // NaN / inf: two-pass path
+    const bool degenerate = n_live_s < 0;   // no unmasked key: uniform attention (see build_live_list)
+    const int nlive = degenerate ? -n_live_s : n_live_s;
+    const float sc_mul = degenerate ? 0.f : QSCALE * q_up * k_up;               // accumulator -> log2-unit score
+    // NaN / inf norms take the two-pass path
+    const bool easy = degenerate || q2max * k2max * (QSCALE * QSCALE) < EASY_BOUND * EASY_BOUND;
     float* att_c = att + (size_t)c * L * 128;
     float* lse_c = lse ? lse + (size_t)c * L * 8 : nullptr;
     // Warp w always runs on SM sub-partition w % 4, and the first warps of a CTA get the extra row block when the
@@ -610,7 +616,7 @@ __device__ __forceinline__ void bwd_load_chunk(const float* __restrict__ base, c
     d.v[p] = ok ? *reinterpret_cast<const float4*>(qp + 256) : z;
     d.g[p] = ok ? *reinterpret_cast<const float4*>(dobase + (size_t)rr * 128 + hg + sub * 4) : z;
     d.o[p] = ok ? *reinterpret_cast<const float4*>(obase + (size_t)rr * 128 + hg + sub * 4) : z;
-    d.lse[p] = (ok && sub == 0) ? lse_c[(size_t)rr * 8 + h] : INFINITY;   // padded queries: 2^(score - inf) == 0
+    d.lse[p] = (ok && sub == 0) ? lse_c[(size_t)rr * 8 + h] : 0.f;
   }
 }
 __device__ __forceinline__ float quad_sum(float x) {
@@ -725,8 +731,12 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
       if (m0_ < 64) bits |= (unsigned long long)bal << m0_;
     }
     if (n == 0) {
+      // nothing unmasked: uniform attention P = 1 / L (see build_live_list); the score scale is zeroed below and
+      // the log-sum-exp log2(L), common to all rows, takes the place of the mask term
       for (int m = lane; m < ngrp; m += 32) S.lidx[m] = m;
-      n = ngrp;
+      const float fill = -log2f((float)L);
+      for (int j = lane; j < L; j += 32) S.Ms[j] = fill;
+      n = -ngrp;
       bits = ~0ull;
     }
     if (lane == 0) n_live_s = n, live_bits_s = bits;
@@ -740,12 +750,13 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
   pow2_scale(__uint_as_float(nrm_bits[1]), 14, k_dn, k_up);
   pow2_scale(__uint_as_float(nrm_bits[2]), 7, v_dn, v_up);
   pow2_scale(__uint_as_float(nrm_bits[3]), 7, g_dn, g_up);
+  const bool degenerate = n_live_s < 0;
   BwdScales sc;
-  sc.cS = QSCALE * q_up * k_up;
+  sc.cS = degenerate ? 0.f : QSCALE * q_up * k_up;
   sc.cQ = 0.25f * g_up * v_up * k_up;
   sc.cK = 0.25f * g_up * v_up * q_up;
   sc.cV = g_up;
-  const float inv_cS = 1.f / sc.cS, d_scale = g_dn * v_dn;
+  const float inv_cS = degenerate ? 0.f : 1.f / sc.cS, d_scale = g_dn * v_dn;
   for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
     if (!single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, row0, L, hg, h, d);
 #pragma unroll
@@ -757,7 +768,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
       bwd_store_images(d.g[p], g_dn, r, Lr, S.Gh, S.Gt, S.TS);
       const float dd = quad_sum(dot4(d.g[p], d.o[p]));   // D = sum_d dO O of the row
       if (r < Lr && (tid & 3) == 0) {
-        const float lm = -(d.lse[p] * LOG2E) * inv_cS, dm = -dd * d_scale;
+        // padded queries: 2^(score - inf) == 0 (with the score scale zeroed, inf * 0 would be a NaN: their Q and dO
+        // rows are zero, a finite start value contributes nothing either)
+        const float lm = r < L ? -(d.lse[p] * LOG2E) * inv_cS : (degenerate ? 0.f : -INFINITY), dm = -dd * d_scale;
         S.Lm[r] = lm;
         S.Dm[r] = dm;
         // accumulator quads of phase B: column (query) r sits at positions (r & 1) and (r & 1) + 2 of quad [r / 8][(r & 7) / 2]
@@ -787,7 +800,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
       }
     }
   }
-  const int nlive = n_live_s;
+  const int nlive = degenerate ? -n_live_s : n_live_s;
   const unsigned long long live_bits = live_bits_s;
   // Warp w always runs on SM sub-partition w % 4: rotate the block assignment per CTA so the sub-partitions stay
   // evenly loaded when the block count is not a multiple of the warp count.

@@ -49,7 +49,9 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 // cvt.rna.tf32.f32 is a 4-instruction sequence on sm_100a (constant, FSETP, predicated IMAD, LOP3); for finite
 // inputs the same result is one integer add (half a TF32 ulp) and one mask.
 __device__ __forceinline__ float tf32_rn(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  const uint32_t b = __float_as_uint(x);
+  // (the add would carry a NaN with an all-ones payload -- what the tensor cores produce -- into -0: keep NaNs as they are)
+  return (b & 0x7fffffffu) > 0x7f800000u ? x : __uint_as_float((b + 0x1000u) & 0xFFFFE000u);
 }
 // operand bits for a tensor-core instruction that truncates to TF32 anyway: the add alone rounds to nearest
 __device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return __float_as_uint(x) + 0x1000u; }
