@@ -45,6 +45,20 @@ constexpr int WG_ONES_BYTES = 64 * 128;          // 64 rows x 128 B of 1.0f: A o
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 256 + 1024;
 constexpr int WG_TMEM_COLS = 512;                // 2 x 128 (dW accumulators) + 2 x 128 (column sums)
 
+#ifdef GEMM_PROFILE
+__device__ long long gemm_prof[16];
+#define GP_T0() long long gp_t = clock64()
+#define GP_ADD(i)                                     \
+  do {                                                \
+    const long long gp_n = clock64();                 \
+    if (blockIdx.x == 0) gemm_prof[i] += gp_n - gp_t; \
+    gp_t = gp_n;                                      \
+  } while (0)
+#else
+#define GP_T0()
+#define GP_ADD(i)
+#endif
+
 struct GemmArgs {
   int M, N, K;
   int n_tiles, k_splits, kb_per_split, num_items;
@@ -132,7 +146,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = ks * g.kb_per_split;
         const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
         for (int kb = kb0; kb < kb1; ++kb) {
+          GP_T0();
           mbar_wait(&empty[stage], phase ^ 1);
+          GP_ADD(0);
           mbar_expect_tx(&full[stage], tx);
           uint8_t* sa = ring + stage * STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
@@ -155,7 +171,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = ks * g.kb_per_split;
         const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
         for (int kb = kb0; kb < kb1; ++kb) {
+          GP_T0();
           mbar_wait(&full[stage], phase);
+          if (threadIdx.x == 0) GP_ADD(1);
           const uint8_t* sa = ring + stage * STAGE_BYTES + row * 128;
           float lo[32];
 #pragma unroll
@@ -164,10 +182,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
             lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
           }
+          if (threadIdx.x == 0) GP_ADD(2);
           tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
+          if (threadIdx.x == 0) GP_ADD(3);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (threadIdx.x == 0) GP_ADD(4);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -186,12 +207,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        {
+          GP_T0();
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          GP_ADD(8);
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+          GP_T0();
           mbar_wait(&full[stage], phase);
+          GP_ADD(5);
           if (g.split) mbar_wait(&lofull[stage], phase);
+          GP_ADD(6);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
           const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
@@ -208,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           umma_commit(&empty[stage]);  // frees the smem stage (and its A_lo columns) when these MMAs are done
+          GP_ADD(7);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);      // accumulator complete
