@@ -306,7 +306,7 @@ __device__ __forceinline__ void raw_row(const float* raw, int r, int L, float4 (
 // the norm bound says the exponentials could leave fp32 range.
 // NW warps per CTA: 2 up to 64 tokens (each warp two row blocks; twice the CTAs in flight), else 4.
 template <bool PV3X, int NW>
-__global__ void __launch_bounds__(NW * 32, 12 / NW) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+__global__ void __launch_bounds__(NW * 32, NW == 5 ? 3 : 12 / NW) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                           int mS, int m0, int L, int nitems, float* __restrict__ att,
                                                           float* __restrict__ lse) {
   constexpr int FWD_WARPS = NW, FWD_THREADS = NW * 32;
@@ -829,10 +829,14 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
   const size_t smem = (size_t)((Lr + Lp) * 16 + (L < 64 ? 32 : 16) * vt_stride(Lp) + Lp + ((nt + 3) & ~3) + 3 * Lp * RS + Lp) *
                       sizeof(float);
   // static smem of the kernel counts against the 227 KB limit too: ask for what is needed
-  static size_t attr_smem[3] = {0, 0, 0};
-  static int ctas_per_sm[3] = {0, 0, 0}, num_sms = 0;
-  const int v = L < 64 ? 0 : (L == 64 ? 1 : 2), nw = v == 2 ? 4 : 2;
-  auto kern = v == 0 ? attn_fwd_kernel<true, 2> : (v == 1 ? attn_fwd_kernel<false, 2> : attn_fwd_kernel<false, 4>);
+  static size_t attr_smem[4] = {0, 0, 0, 0};
+  static int ctas_per_sm[4] = {0, 0, 0, 0}, num_sms = 0;
+  static size_t attr_smem5 = 0;
+  const int nblk = Lr / 16;
+  const int v = L < 64 ? 0 : (L == 64 ? 1 : (nblk == 9 || nblk == 10 ? 3 : 2)), nw = v == 3 ? 5 : (v == 2 ? 4 : 2);
+  auto kern = v == 0 ? attn_fwd_kernel<true, 2>
+                     : (v == 1 ? attn_fwd_kernel<false, 2> : (v == 2 ? attn_fwd_kernel<false, 4> : attn_fwd_kernel<false, 5>));
+  (void)attr_smem5;
   if (smem > attr_smem[v] || ctas_per_sm[v] == 0) {
     TPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[v] = smem;
