@@ -533,7 +533,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int m_t = m0; m_t < m_tiles; m_t += groups) {
         for (int kb = 0; kb < C::NKB; ++kb) {
+          GP_T0();
           mbar_wait(&empty[stage], phase ^ 1);
+          GP_ADD(0);
           mbar_expect_tx(&full[stage], TILE_BYTES);
           tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, m_t * BM);
           if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
@@ -547,7 +549,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int m_t = m0; m_t < m_tiles; m_t += groups) {
         for (int kb = 0; kb < C::NKB; ++kb) {
+          GP_T0();
           mbar_wait(&full[stage], phase);
+          if (threadIdx.x == 0) GP_ADD(1);
           const uint8_t* sa = ring + stage * TILE_BYTES + row * 128;
           float lo[32];
 #pragma unroll
@@ -560,6 +564,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (threadIdx.x == 0) GP_ADD(2);
           if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -574,12 +579,19 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        {
+          GP_T0();
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          GP_ADD(8);
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < C::NKB; ++kb) {
+          GP_T0();
           mbar_wait(&full[stage], phase);
+          GP_ADD(5);
           if (SPLIT) mbar_wait(&lofull[stage], phase);
+          GP_ADD(6);
           tc_fence_after();
           const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + stage * TILE_BYTES), 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES), 16, 1024);
@@ -594,6 +606,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           umma_commit(&empty[stage]);
+          GP_ADD(7);
           if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -612,7 +625,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        GP_T0();
         mbar_wait(&tfull[acc], acc_phase);
+        if (leader) GP_ADD(9);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -638,13 +653,16 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
           // older stores may still be in flight when the threads are released
+          if (leader) GP_ADD(10);
           if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 2) : "memory");
+          if (leader) GP_ADD(11);
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (leader) {
             tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
             tma_store_commit();
           }
+          if (leader) GP_ADD(12);
         }
       }
       if (leader) tma_store_wait_all0();
