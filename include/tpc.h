@@ -203,6 +203,38 @@ int tpc_a2c_grads(tpc_model* m, const float* actor_shadow, const float* actor_pa
 int tpc_adam_apply(tpc_model* m, int which, float* params, const float* grads, float* adam_m, float* adam_v, int step,
                    float lr, float clipnorm, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * tester: batched heuristics and solution statistics (environment/custom/resource_v3/tester.py:117-255)
+ * One warp per instance; the reference solves one instance at a time with Python Node / Resource objects and
+ * asserts batch == 1 (heuristic/base_heuristic.py:39,59).
+ * state: (B, >= num_bins + num_resources rows, >= 3 features) fp32, instance stride ld_instance and row stride
+ * ld_row in floats; row 0 is the EOS node. assign (B, num_resources) int32: node id per rule in the ORIGINAL
+ * rule order, 0 = rejected. remaining (B, num_bins, 3): node resources after the placement.
+ * ---------------------------------------------------------------------------------------------------- */
+/* replaces DominantResourceHeuristic.solve (heuristic/dominant_heuristic.py:30-71): rules in (stable) order of
+ * max(CPU,RAM,MEM), each to the feasible node with the largest / smallest dominant remainder (node.py:36-70). */
+int tpc_heuristic_dominant(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                           int num_resources, int resource_sort_descending, int node_sort_descending, int32_t* assign,
+                           float* remaining, void* stream);
+/* replaces RandomHeuristic.solve (heuristic/random_heuristic.py:28-65): the i-th random.randrange(n) call of
+ * instance b is floor(u * n / 2^32) with u = word i of the Philox4x32-10 stream (seed, instance_id0 + b, epoch,
+ * kind 4). */
+int tpc_heuristic_random(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                         int num_resources, uint64_t seed, int64_t instance_id0, int64_t epoch, int32_t* assign,
+                         float* remaining, void* stream);
+/* replaces compute_stats (misc/utils.py:56-81) for every instance: dominant = min remaining resource over the
+ * real nodes (unrounded), rejected = rules at node 0, empty_nodes = real nodes without a rule. assign is read as
+ * assign[b * stride_instance + j * stride_rule] (the net's step-major actions (T,B): strides 1 and B). */
+int tpc_solution_stats(tpc_handle* h, const int32_t* assign, int64_t stride_instance, int64_t stride_rule,
+                       const float* remaining, int ld_instance, int ld_row, int B, int num_bins, int num_resources,
+                       float* dominant, int32_t* rejected, int32_t* empty_nodes, void* stream);
+/* replaces gather_stats_from_solutions (misc/utils.py:97-159): heur_* are (num_heuristics, B). Adds to
+ * results[0..2] the dominant {won, draw, lost} and to results[3..5] the rejected {won, draw, lost} counts of the
+ * net against the best heuristic; net_dominant_rounded (B, optional) = round_half_up(net_dominant, 2). */
+int tpc_compare_solutions(tpc_handle* h, const float* net_dominant, const int32_t* net_rejected,
+                          const float* heur_dominant, const int32_t* heur_rejected, int num_heuristics, int B,
+                          float* net_dominant_rounded, int32_t* results, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,48 @@ def solution_stats(assign, rem):
     used[assign] = True
     empty = int((~used[1:]).sum())
     return dominant, rejected, empty
+
+
+# ---- Philox4x32-10 (Salmon et al. 2011): replays the device kernel's random.randrange substitute -----------------
+_M0, _M1, _W0, _W1, _MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+
+
+def philox4x32_10(counter, key):
+    c = [int(x) & _MASK for x in counter]
+    k0, k1 = int(key[0]) & _MASK, int(key[1]) & _MASK
+    for _ in range(10):
+        p0, p1 = _M0 * c[0], _M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k0, p1 & _MASK, (p0 >> 32) ^ c[3] ^ k1, p0 & _MASK]
+        k0, k1 = (k0 + _W0) & _MASK, (k1 + _W1) & _MASK
+    return c
+
+
+def philox_randrange(seed, instance_id, epoch, kind=4):
+    """randrange(n) of instance `instance_id`: call i returns floor(u_i * n / 2^32), u_i = word i % 4 of Philox block
+    i // 4 with counter (id lo, id hi, epoch, kind << 28 | block) and key (seed lo, seed hi) -- the layout of the
+    device streams (csrc/philox.cuh)."""
+    state = {"i": 0, "blk": -1, "cur": None}
+
+    def randrange(n):
+        i = state["i"]
+        state["i"] += 1
+        b = i >> 2
+        if b != state["blk"]:
+            state["cur"] = philox4x32_10((instance_id & _MASK, (instance_id >> 32) & _MASK, epoch & _MASK,
+                                          ((kind << 28) | b) & _MASK), (seed & _MASK, (seed >> 32) & _MASK))
+            state["blk"] = b
+        return (state["cur"][i & 3] * n) >> 32
+    return randrange
+
+
+def compare_solutions(net_dominant, net_rejected, heur_dominant, heur_rejected):
+    """gather_stats_from_solutions' verdict (misc/utils.py:107-157) for one instance:
+    (rounded net dominant, dominant code, rejected code), codes 0 won / 1 draw / 2 lost."""
+    nd = rhu2(net_dominant)
+    max_dom, min_rej = F32(-1), 9999
+    for d, r in zip(heur_dominant, heur_rejected):
+        max_dom = max(max_dom, rhu2(d))
+        min_rej = min(min_rej, int(r))
+    cd = 2 if max_dom > nd else (1 if max_dom == nd else 0)
+    cr = 2 if min_rej < net_rejected else (1 if min_rej == net_rejected else 0)
+    return nd, cd, cr

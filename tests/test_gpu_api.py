@@ -84,8 +84,8 @@ def test_trainer_and_tester_run(tmp_path):
     tcfg["show_per_test_stats"] = False
     tcfg["testbed"].update(num_tests=1, node_sample_configs={"min": 5, "max": 10, "step": 5},
                            request_sample_configs={"min": 10, "max": 20, "step": 10})
-    dominant, rejected = tester(env, agent, tcfg, str(tmp_path))
-    assert dominant.shape == rejected.shape == (2 * 2 * 4,)
+    dominant, rejected = tester(env, agent, tcfg, str(tmp_path))     # [won, draw, lost] vs the best heuristic
+    assert dominant.shape == rejected.shape == (3,) and dominant.sum() == rejected.sum() == 2 * 2 * 4
     assert os.path.exists(os.path.join(str(tmp_path), "tests", "test.csv"))
 
 

@@ -46,3 +46,23 @@ def test_reference_unit_test_instance():
     np.testing.assert_array_equal(a, G["kat_assign"])
     np.testing.assert_array_equal(a, [2, 0])
     np.testing.assert_array_equal(r[1:], G["kat_rem"][1:])
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors, philox4x32-10."""
+    assert oh.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oh.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oh.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    rr = oh.philox_randrange(1235, 7, 0)
+    draws = [rr(n) for n in (1, 2, 3, 50, 100, 7, 7, 7, 7)]
+    assert draws[0] == 0 and all(0 <= d < n for d, n in zip(draws, (1, 2, 3, 50, 100, 7, 7, 7, 7)))
+
+
+def test_compare_solutions_follows_reference_thresholds():
+    """misc/utils.py:116-157: heuristics start from max_dominant = -1 / min_rejected = 9999."""
+    nd, cd, cr = oh.compare_solutions(np.float32(0.104999), 3, [np.float32(0.10), np.float32(0.05)], [4, 3])
+    assert float(nd) == float(np.float32(0.10)) and (cd, cr) == (1, 1)
+    assert oh.compare_solutions(np.float32(0.2), 1, [np.float32(0.3)], [0])[1:] == (2, 2)
+    assert oh.compare_solutions(np.float32(0.2), 1, [np.float32(0.1)], [2])[1:] == (0, 0)
+    assert oh.compare_solutions(np.float32(0.0), 0, [], [])[1:] == (0, 0)     # no heuristic: -1 < 0 and 9999 > 0

@@ -264,8 +264,8 @@ class KnapsackEnvironmentV2(_DeviceEnvBase):
 
 def env_factory(type: str, name: str, opts: dict, device="cuda:0"):
     """environment/env_factory.py:27-33 -> (env, tester)."""
-    from .tester import test as resource_tester
-    table = {"ResourceV3": (ResourceEnvironmentV3, resource_tester), "KnapsackV2": (KnapsackEnvironmentV2, resource_tester)}
+    from .tester import knapsack_test, test as resource_tester
+    table = {"ResourceV3": (ResourceEnvironmentV3, resource_tester), "KnapsackV2": (KnapsackEnvironmentV2, knapsack_test)}
     if type != "custom" or name not in table:
         raise NameError(f"Unknown environment {type}/{name}")
     env_cls, tester = table[name]

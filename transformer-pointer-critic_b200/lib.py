@@ -83,6 +83,14 @@ SIGNATURES = {
                               c_void_p, c_size_t, c_void_p]),
     "tpc_adam_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                c_float, c_void_p]),
+    "tpc_heuristic_dominant": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p]),
+    "tpc_heuristic_random": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_i64, c_i64,
+                                     c_void_p, c_void_p, c_void_p]),
+    "tpc_solution_stats": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tpc_compare_solutions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p]),
 }
 
 _lib = None
