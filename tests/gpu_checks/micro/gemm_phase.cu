@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   float ms = 0;
   for (int rep = 0; rep < 4; ++rep) {
 #ifdef GEMM_PROFILE
-    long long z[16] = {0};
+    unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(tpc::gemm_prof, z, sizeof(z));
 #endif
     cudaEventRecord(e0);
@@ -39,16 +39,25 @@ int main(int argc, char** argv) {
     if (rc) { printf("rc %d\n", rc); return 1; }
     cudaEventElapsedTime(&ms, e0, e1);
   }
-  long long pr[16] = {0};
+  unsigned long long pr[16] = {0};
 #ifdef GEMM_PROFILE
   cudaMemcpyFromSymbol(pr, tpc::gemm_prof, sizeof(pr));
 #endif
   const double kbs = (double)((M + 127) / 128) * (N / 128) / 148 * (K / 32);   // k-blocks of CTA 0
   printf("M=%d K=%d split=%d ln=%d: %.1f us, %.0f k-blocks per CTA -> %.0f clk per k-block at 1.9 GHz\n", M, K, split, ln, ms * 1e3, kbs,
          ms * 1e-3 * 1.9e9 / kbs);
+#ifdef GEMM_CLOCKS
+  long long ck[2] = {0, 0};
+  cudaMemcpyFromSymbol(ck, tpc::gemm_clk, sizeof(ck));
+  if (ck[1] > 0) printf("  CTA 0 MMA issuer: %lld clk in %lld ns -> SM clock %.3f GHz, %.0f clk per k-block (measured clock)\n", ck[0], ck[1],
+                        (double)ck[0] / ck[1], ck[0] / kbs);
+#endif
   const char* nm[13] = {"producer: wait empty", "splitter: wait full", "splitter: lds+alu", "splitter: tmem st+wait",
                        "splitter: fence+arrive", "mma: wait full", "mma: wait lofull", "mma: issue+commit", "mma: wait tempty (per tile)",
                        "epilogue: wait tfull", "epilogue: chunk ld+math+sts", "epilogue: wait store read", "epilogue: barrier+store"};
+  if (pr[14]) printf("  TMA issue -> data seen by a waiting splitter: %.0f clk average over %llu k-blocks\n", (double)pr[13] / pr[14], pr[14]);
+  if (pr[14]) printf("  commit issued -> producer sees the stage empty: %.0f clk; TMA age when the MMA issuer reaches the stage: %.0f clk (bres kernels; epilogue slot 12 unused there)\n",
+                     (double)pr[15] / pr[14], (double)pr[12] / pr[14]);
   for (int i = 0; i < 13; ++i) printf("  %-30s %8.0f clk per k-block\n", nm[i], pr[i] / kbs);
   return 0;
 }

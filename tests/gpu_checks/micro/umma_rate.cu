@@ -11,10 +11,11 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
+  __shared__ uint64_t bars[4];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (6 * 16384 + 2 * 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc<512>(&slot);
   tc_fence_before();
   __syncthreads();
@@ -38,7 +39,14 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
           umma_tf32_ss(tm, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
           umma_tf32_ts(tm, tm + 256 + st * 32 + 8 * kk, db + 2 * kk, idesc, 1u);
         }
+        if (MODE >= 3) {   // all-TS triple as issued by the GEMM kernels
+          umma_tf32_ts(tm, tm + 384 + st * 32 + 8 * kk, db + 2 * kk, idesc, 1u);
+          umma_tf32_ts(tm, tm + 384 + st * 32 + 8 * kk, dbl + 2 * kk, idesc, 1u);
+          umma_tf32_ts(tm, tm + 256 + st * 32 + 8 * kk, db + 2 * kk, idesc, 1u);
+        }
       }
+      if (MODE >= 4) umma_commit(&bars[st]);          // per-k-block commit to a stage barrier (never waited on)
+      if (MODE >= 5) { mbar_try_wait(&bars[3], 1); tc_fence_after(); }   // the wait + fence of the next k-block
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0);
@@ -58,7 +66,7 @@ void run(const char* name, long long* d) {
     k<MODE, N><<<grid, 128, smem>>>(iters, d);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    const double n_mma = iters * 4.0 * (MODE == 2 ? 3 : 1);
+    const double n_mma = iters * 4.0 * (MODE >= 2 ? 3 : 1);
     printf("%-28s grid %3d: %7.1f clk per UMMA (M=128 N=%d K=8) -> %.0f TFLOP/s at 148 SMs x 1.9 GHz  [%s]\n", name, grid,
            h / n_mma, N, 2.0 * 128 * N * 8 / (h / n_mma) * 148 * 1.9e9 / 1e12, cudaGetErrorString(cudaGetLastError()));
   }
@@ -69,5 +77,8 @@ int main() {
   run<0, 256>("SS", d);
   run<1, 128>("TS (A in TMEM)", d);
   run<2, 128>("3xTF32 triple SS,SS,TS", d);
+  run<3, 128>("3xTF32 triple TS,TS,TS", d);
+  run<4, 128>("  + commit per k-block", d);
+  run<5, 128>("  + try_wait + fence", d);
   return 0;
 }

@@ -98,8 +98,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must not hang the GPU box (gpurun strikes). ~2^28 probes then trap.
+// Wait for the phase with the given parity. The spin loop is written in PTX: a C++ loop around try_wait that also
+// counts its probes compiles to YIELD + TRYWAIT + bookkeeping and costs ~190 clocks even when the barrier completed
+// long ago (tests/gpu_checks/micro/umma_queue.cu); this form costs ~40. tcgen05.mma issue is nearly synchronous
+// (the issuing thread runs at most one or two MMAs ahead of the tensor pipe), so every clock the MMA warp spends in
+// a satisfied wait is a clock the tensor pipe idles.
+// -DTPC_BOUNDED_WAIT restores the counted loop that traps after 2^26 probes (pipeline debugging on a shared GPU box).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef TPC_BOUNDED_WAIT
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
@@ -107,6 +113,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       asm volatile("trap;");
     }
   }
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TPC_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TPC_WAIT_DONE;\n\t"
+      "bra TPC_WAIT_LOOP;\n\t"
+      "TPC_WAIT_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,6 +244,25 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
       "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
       "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])),
+      "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+      "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])),
+      "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])),
+      "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]  (A: lane = row, one 32-bit column per K element)
+// same store without the wait: a later tmem_st_32x32 (or tcgen05.wait::st) completes both
+__device__ __forceinline__ void tmem_st_32x32_nowait(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
       ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
       "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
       "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),

@@ -27,7 +27,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BK = 32;                        // fp32 columns per k-block == one 128-byte swizzle span
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;                     // 3xTF32 mode: 3 stages of A + B + B_lo (48 KB)
+constexpr int STAGES_1P = 4;                  // single-pass mode: 4 stages of A + B (32 KB) in the same ring space
+constexpr int MAX_STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // A + B (+ B_lo in 3xTF32 mode)
 constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
@@ -35,7 +37,8 @@ constexpr int GEMM_THREADS = 320;             // warps 0-3 A_lo splitters, 4-7 e
 constexpr int WG_THREADS = 256;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
 constexpr int TMEM_COLS = 512;                // 2 x 128 accumulators + STAGES x 32 columns of A_lo
-constexpr int TMEM_ALO = 256;                 // first A_lo column
+constexpr int TMEM_ALO = 256;                 // first A_lo column (32 per stage)
+constexpr int TMEM_AHI = 384;                 // first column of the raw A k-blocks (32 per stage, <= 4 stages)
 
 constexpr int WG_TB = 32;                     // tokens per wgrad stage (4 MMAs of K=8)
 constexpr int WG_STAGES = 6;
@@ -46,17 +49,33 @@ constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 256 + 1024;
 constexpr int WG_TMEM_COLS = 512;                // 2 x 128 (dW accumulators) + 2 x 128 (column sums)
 
 #ifdef GEMM_PROFILE
-__device__ long long gemm_prof[16];
+// phase timing: every role thread accumulates its clock64 intervals in registers (a global read-modify-write per
+// stamp would add its own latency to the next interval) and CTA 0 flushes them once at the end of the kernel
+__device__ unsigned long long gemm_prof[16];
+#define GP_DECL() long long gp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define GP_T0() long long gp_t = clock64()
-#define GP_ADD(i)                                     \
-  do {                                                \
-    const long long gp_n = clock64();                 \
-    if (blockIdx.x == 0) gemm_prof[i] += gp_n - gp_t; \
-    gp_t = gp_n;                                      \
+#define GP_ADD(i)                        \
+  do {                                   \
+    const long long gp_n = clock64();    \
+    gp_acc[i] += gp_n - gp_t;            \
+    gp_t = gp_n;                         \
+  } while (0)
+#define GP_FLUSH()                                                                                      \
+  do {                                                                                                  \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                                    \
+      _Pragma("unroll") for (int gp_i = 0; gp_i < 16; ++gp_i)                                           \
+        if (gp_acc[gp_i]) atomicAdd(&gemm_prof[gp_i], (unsigned long long)gp_acc[gp_i]);                 \
+    }                                                                                                   \
   } while (0)
 #else
+#define GP_DECL()
 #define GP_T0()
 #define GP_ADD(i)
+#define GP_FLUSH()
+#endif
+
+#ifdef GEMM_CLOCKS
+__device__ long long gemm_clk[2];   // SM clocks and nanoseconds of CTA 0's MMA issuer (clock-rate probe)
 #endif
 
 struct GemmArgs {
@@ -90,17 +109,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* ring = smem;
   uint8_t* epi = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* full = bars;                 // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* tfull = bars + 2 * MAX_STAGES;  // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* auxfull = tempty + 2;        // [1]
-  uint64_t* lofull = auxfull + 1;        // [STAGES] A_lo of the stage is in TMEM
-  uint64_t* auxbox = lofull + STAGES;    // [4] streaming epilogue: aux chunk of a staging box landed
+  uint64_t* lofull = auxfull + 1;        // [MAX_STAGES] A_lo of the stage is in TMEM
+  uint64_t* auxbox = lofull + MAX_STAGES;  // [4] streaming epilogue: aux chunk of a staging box landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbox + 4);
+  // ring geometry: the HBM latency is hidden by bytes in flight, so the single-pass mode (no B_lo tile) turns the
+  // spare third of each stage into a fourth stage
+  const int nstages = g.split ? STAGES : STAGES_1P;
+  const int stage_bytes = g.split ? STAGE_BYTES : 2 * TILE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  GP_DECL();
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -110,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.aux_mode) tma_prefetch_desc(&tmAux);
   }
   if (warp == 9 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
       mbar_init(&lofull[s], 4);
@@ -150,11 +174,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           GP_ADD(0);
           mbar_expect_tx(&full[stage], tx);
-          uint8_t* sa = ring + stage * STAGE_BYTES;
+          uint8_t* sa = ring + stage * stage_bytes;
+#ifdef GEMM_DBG_L2_A   // experiment: every A tile comes from row tile 0 (L2 hit) -- separates HBM latency from on-chip limits
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, 0);
+#else
           tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
+#endif
           tma_load_2d(sa + TILE_BYTES, &tmB, &full[stage], kb * BK, n_t * BN);
           if (g.split) tma_load_2d(sa + 2 * TILE_BYTES, &tmBlo, &full[stage], kb * BK, n_t * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -174,22 +202,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           GP_T0();
           mbar_wait(&full[stage], phase);
           if (threadIdx.x == 0) GP_ADD(1);
-          const uint8_t* sa = ring + stage * STAGE_BYTES + row * 128;
-          float lo[32];
+          const uint8_t* sa = ring + stage * stage_bytes + row * 128;
+          float lo[32], hi[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
+            hi[c * 4 + 0] = a.x; hi[c * 4 + 1] = a.y; hi[c * 4 + 2] = a.z; hi[c * 4 + 3] = a.w;
             lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
             lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
           }
           if (threadIdx.x == 0) GP_ADD(2);
+          tmem_st_32x32_nowait(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_AHI + stage * BK, hi);
           tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
           if (threadIdx.x == 0) GP_ADD(3);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&lofull[stage]);
           if (threadIdx.x == 0) GP_ADD(4);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -218,26 +248,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           GP_T0();
           mbar_wait(&full[stage], phase);
           GP_ADD(5);
-          if (g.split) mbar_wait(&lofull[stage], phase);
-          GP_ADD(6);
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
           const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(sa + TILE_BYTES, 16, 1024);
           const uint64_t dbl = umma_smem_desc_sw128(sa + 2 * TILE_BYTES, 16, 1024);
           const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
+          if (g.split) {
+            // 3xTF32: all three products take A from TMEM (raw and low k-block, parked there by the splitter warps).
+            // An SS-mode TF32 MMA reads 4 KB of A and 4 KB of B from shared memory every 64 clocks -- the whole
+            // 128 B/clk of the SM -- so with A in TMEM the twelve MMAs of a k-block read 48 KB instead of 80 KB and
+            // leave room for the TMA writes and the epilogue staging traffic.
+            mbar_wait(&lofull[stage], phase);
+            GP_ADD(6);
+            tc_fence_after();
+            const uint32_t tahi = tmem_base + TMEM_AHI + stage * BK;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // advance 8 fp32 (32 B) along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-            umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (g.split) {
-              umma_tf32_ss(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1u);       // trunc(A) . B_lo
-              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);     // A_lo . trunc(B)
+            for (int k = 0; k < BK / 8; ++k) {
+              // advance 8 fp32 (32 B) along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+              umma_tf32_ts(tmem_d, tahi + 8 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);  // trunc(A) . trunc(B)
+              umma_tf32_ts(tmem_d, tahi + 8 * k, dbl + 2 * k, idesc, 1u);                            // trunc(A) . B_lo
+              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);                             // A_lo . trunc(B)
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem stage (and its A_lo columns) when these MMAs are done
           GP_ADD(7);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);      // accumulator complete
       }
@@ -442,6 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  GP_FLUSH();
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -472,6 +513,10 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
   using C = Bres<SPLIT>;
+#ifdef GEMM_PROFILE
+  __shared__ volatile long long gp_issue_t[8];
+  __shared__ volatile long long gp_commit_t[8];
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bsm = smem;
@@ -489,6 +534,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  GP_DECL();
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -537,7 +583,15 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           GP_ADD(0);
           mbar_expect_tx(&full[stage], TILE_BYTES);
+#ifdef GEMM_PROFILE
+          if (phase || m_t != m0) { gp_acc[15] += clock64() - gp_commit_t[stage]; }
+          gp_issue_t[stage] = clock64();
+#endif
+#ifdef GEMM_DBG_L2_A
+          tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, 0);
+#else
           tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, m_t * BM);
+#endif
           if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -552,15 +606,22 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           GP_T0();
           mbar_wait(&full[stage], phase);
           if (threadIdx.x == 0) GP_ADD(1);
+#ifdef GEMM_PROFILE
+          if (threadIdx.x == 0) { gp_acc[13] += clock64() - gp_issue_t[stage]; gp_acc[14] += 1; }
+#endif
+#ifndef GEMM_DBG_NOST
           const uint8_t* sa = ring + stage * TILE_BYTES + row * 128;
-          float lo[32];
+          float lo[32], hi[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
+            hi[c * 4 + 0] = a.x; hi[c * 4 + 1] = a.y; hi[c * 4 + 2] = a.z; hi[c * 4 + 3] = a.w;
             lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
             lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
           }
+          tmem_st_32x32_nowait(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_AHI + stage * BK, hi);
           tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
+#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&lofull[stage]);
@@ -573,6 +634,11 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
       mbar_wait(bfull, 0);
+#ifdef GEMM_CLOCKS
+      const long long gc0 = clock64();
+      unsigned long long gt0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -588,29 +654,49 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < C::NKB; ++kb) {
           GP_T0();
+#ifdef GEMM_PROFILE
+          gp_acc[12] += clock64() - gp_issue_t[stage];   // age of this stage's TMA when the issuer gets to it
+#endif
           mbar_wait(&full[stage], phase);
           GP_ADD(5);
-          if (SPLIT) mbar_wait(&lofull[stage], phase);
-          GP_ADD(6);
           tc_fence_after();
           const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + stage * TILE_BYTES), 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES), 16, 1024);
           const uint64_t dbl = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES + TILE_BYTES), 16, 1024);
           const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
+          if (SPLIT) {   // all three products with A from TMEM (see gemm_tc_kernel)
+            mbar_wait(&lofull[stage], phase);
+            GP_ADD(6);
+            tc_fence_after();
+            const uint32_t tahi = tmem_base + TMEM_AHI + stage * BK;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (SPLIT) {
-              umma_tf32_ss(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1u);
+            for (int k = 0; k < BK / 8; ++k) {
+              umma_tf32_ts(tmem_d, tahi + 8 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(tmem_d, tahi + 8 * k, dbl + 2 * k, idesc, 1u);
               umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
+#ifdef GEMM_PROFILE
+          gp_commit_t[stage] = clock64();
+#endif
           GP_ADD(7);
           if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
       }
+#ifdef GEMM_CLOCKS
+      if (blockIdx.x == 0) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        gemm_clk[0] = clock64() - gc0;
+        gemm_clk[1] = (long long)(gt1 - gt0);
+      }
+#endif
     }
   } else if (warp >= 4 && warp < 8) {
     const int et = threadIdx.x - 128;
@@ -630,6 +716,12 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) GP_ADD(9);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#ifdef GEMM_DBG_NOEPI
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+#endif
 #pragma unroll 1
         for (int c = 0; c < 4; ++c, ++cidx) {
           uint8_t* box = epi + (cidx % NBUF) * TILE_BYTES;
@@ -662,7 +754,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
             tma_store_commit();
           }
-          if (leader) GP_ADD(12);
+          if (leader) GP_ADD(11);
         }
       }
       if (leader) tma_store_wait_all0();
@@ -726,6 +818,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  GP_FLUSH();
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem_base);
