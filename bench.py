@@ -96,10 +96,12 @@ def run_reference(args):
     sample = "per step: 2 rollout steps + critic/actor forward-backward-Adam on 256 states at 50 nodes x 100 rules"
     print(json.dumps({
         "impl": "reference", "metric": "ResourceV3 placement decisions/sec (rollout+A2C update)", "value": v,
-        "unit": "decisions/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ResourceV3 50 nodes x 100 rules, batch 1024/GPU, rollout + A2C update", "timing": sample},
+        "config": {"workload": f"ResourceV3 {WORKLOAD['nodes']} nodes x {WORKLOAD['rules']} rules, batch "
+                               f"{WORKLOAD['batch_per_gpu']}/GPU, greedy reward, rollout + A2C update (actor 1 layer, "
+                               f"critic 3 layers)", "timing": sample},
         "cpu_baseline": {"value": v, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -288,10 +290,17 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="states per update chunk (default: ~10240, equal chunks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: native libraries (the NCCL version banner, for instance) write to file
+    # descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and Python's sys.stdout keeps the real one.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -159,3 +159,22 @@ def test_knapsack_v2_trains_on_the_same_kernels(tmp_path):
     assert done and np.array_equal(bufs.batch.cpu().numpy(), state)
     out = trainer(env, agent, dict(trainer_cfg, n_iterations=2), False, str(tmp_path))
     assert all(np.isfinite(v) for buf in out for v in buf)
+
+
+def test_runner_writes_the_reference_artefacts(tmp_path):
+    """main.py:40-83: config.json, env.txt, training/logs.csv, model/actor.npz, tests/test.csv."""
+    from tpc_b200.main import runner
+    ov = {"trainer_config": {"n_iterations": 2},
+          "env_config": {"batch_size": 8, "node_sample_size": 4, "profiles_sample_size": 6},
+          "tester_config": {"batch_size": 3, "show_per_test_stats": False, "show_inference_progress": False,
+                            "testbed": {"num_tests": 1, "node_sample_configs": {"min": 5, "max": 5, "step": 5},
+                                        "node_available_resources": {"min": 0, "max": 100, "step": 100},
+                                        "request_sample_configs": {"min": 10, "max": 10, "step": 10}}}}
+    log_dir, history, (dom, rej) = runner(env_name="ResourceV3", log_root=str(tmp_path), overrides=ov)
+    assert json.load(open(os.path.join(log_dir, "config.json")))["env_config"]["num_profiles"] == 1000
+    assert np.loadtxt(os.path.join(log_dir, "env.txt")).shape == (1000, 3)
+    logs = open(os.path.join(log_dir, "training", "logs.csv")).read().splitlines()
+    assert logs[0] == "Step;Avg Reward;Max Reward;Min Reward;Value Loss;Bin Entropy;Total Bin Loss;Bin Policy Loss"
+    assert len(logs) == 3 and logs[1].startswith("0;") and len(logs[1].split(";")) == 8
+    assert os.path.exists(os.path.join(log_dir, "model", "actor.npz"))
+    assert os.path.exists(os.path.join(log_dir, "tests", "test.csv")) and dom.sum() == rej.sum() == 3

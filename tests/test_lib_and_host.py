@@ -78,3 +78,14 @@ def test_engine_fails_loudly_without_gpu():
     from tpc_b200.engine import Engine
     with pytest.raises(L.TpcError):
         Engine(L.ModelConfig(), "cuda:0")
+
+
+def test_training_log_csv_matches_reference_layout(tmp_path):
+    """agents/plotter.py:99-126."""
+    from tpc_b200.main import log_training_stats
+    data = ([1.0, 2.5], [0.0, 1.0], [3.0, 4.0], [10.12345, 9.0], [0.5, 0.25], [0.75, 0.5], [1.6, 1.5])
+    log_training_stats(data, str(tmp_path), "logs")
+    lines = open(tmp_path / "logs.csv").read().splitlines()
+    assert lines[0] == "Step;Avg Reward;Max Reward;Min Reward;Value Loss;Bin Entropy;Total Bin Loss;Bin Policy Loss"
+    assert lines[1] == "0;1.000;3.000;0.000;10.123;1.600;0.750;0.500"
+    assert lines[2] == "1;2.500;4.000;1.000;9.000;1.500;0.500;0.250"
