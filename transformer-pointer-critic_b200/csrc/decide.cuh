@@ -1,0 +1,30 @@
+// Fused per-step decision kernel of the rollout (decide.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tpc {
+
+struct DecideArgs {
+  // pointer head inputs (see pointer_fwd in kernels.cuh)
+  const float *w1d, *kvw, *V, *bV;
+  float clipC;
+  int has_clip;
+  const float* ptr_mask;   // feasible mask of THIS step (C, S)
+  float *score, *logits;   // optional outputs
+  // pick
+  int greedy;
+  uint64_t seed;
+  int64_t id0, draw;
+  int32_t* actions;        // (C) slot of this step
+  // environment (live state, in place)
+  tpc_env_config env;
+  float *batch, *bin_mask, *mha_mask, *is_empty;
+  int N, R, t;             // nodes incl. EOS, rules (= steps), this step
+  float* rewards;          // (C, R)
+  // inputs of step t + 1 (written unless t + 1 == R); the three *_next trajectory slots may be NULL
+  float *dec_next, *pmask_next, *states_next, *mha_next, *is_empties_next;
+};
+
+int decide_step(const DecideArgs& a, int C, cudaStream_t st);
+
+}  // namespace tpc

@@ -2,6 +2,7 @@
 // decoder cross-attention (one query per state), pointer head, value head, losses.
 // Memory-bound row kernels: one warp per 128-float row (float4 per lane, coalesced 512 B), grid-stride.
 #include "kernels.cuh"
+#include "pointer_dev.cuh"
 
 namespace tpc {
 
@@ -242,69 +243,9 @@ __global__ void __launch_bounds__(256) pointer_fwd_kernel(const float* __restric
   __shared__ float sl[XA_MAX_S];
   __shared__ float red[8];
   __shared__ int redi[8];
-  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4 wd = reinterpret_cast<const float4*>(w1d + (size_t)c * 128)[lane];
-  const float4 v = __ldg(reinterpret_cast<const float4*>(V) + lane);
-  const float bv = __ldg(bV);
-  for (int j = warp; j < S; j += 8) {
-    const float4 we = reinterpret_cast<const float4*>(kvw + ((size_t)c * S + j) * 384 + 256)[lane];
-    float s = v.x * tanhf(wd.x + we.x);
-    s = fmaf(v.y, tanhf(wd.y + we.y), s);
-    s = fmaf(v.z, tanhf(wd.z + we.z), s);
-    s = fmaf(v.w, tanhf(wd.w + we.w), s);
-    s = warp_sum(s) + bv;
-    if (lane == 0) {
-      float l = has_clip ? clipC * tanhf(s) : s;
-      l -= ptr_mask[(size_t)c * S + j] * BIG_NUMBER;
-      sl[j] = l;
-      if (score) score[(size_t)c * S + j] = s;
-      if (logits) logits[(size_t)c * S + j] = l;
-    }
-  }
-  __syncthreads();
-  // softmax over S + argmax(probs) (lowest index wins, tf.argmax)
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < S; j += 256) mx = fmaxf(mx, sl[j]);
-  mx = warp_max(mx);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < S; j += 256) {
-    const float e = expf(sl[j] - mx);
-    sl[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) red[warp] = sum;
-  __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) sum += red[w];
-  float best = -1.f;
-  int besti = 0x7fffffff;
-  for (int j = threadIdx.x; j < S; j += 256) {
-    const float p = sl[j] / sum;
-    if (probs) probs[(size_t)c * S + j] = p;
-    if (p > best) { best = p; besti = j; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-  }
-  __syncthreads();
-  if (lane == 0) { red[warp] = best; redi[warp] = besti; }
-  __syncthreads();
-  if (threadIdx.x == 0 && argmax) {
-    for (int w = 1; w < 8; ++w)
-      if (red[w] > best || (red[w] == best && redi[w] < besti)) { best = red[w]; besti = redi[w]; }
-    argmax[c] = besti;
-  }
+  const int c = blockIdx.x;
+  const int best = pointer_head(c, w1d, kvw, V, bV, clipC, has_clip, ptr_mask, S, score, logits, probs, sl, red, redi);
+  if (threadIdx.x == 0 && argmax) argmax[c] = best;
 }
 
 __global__ void __launch_bounds__(256) pointer_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ score,

@@ -11,6 +11,7 @@
 #include "model.cuh"
 #include "kernels.cuh"
 #include "env.cuh"
+#include "decide.cuh"
 
 using namespace tpc;
 
@@ -257,8 +258,10 @@ struct ActorActs {
   float *w1d = nullptr, *score = nullptr;
 };
 
+// fuse != nullptr (rollout): the pointer head runs inside the fused decision kernel (decide.cu) together with the
+// pick, the environment step and the staging of the next step's inputs
 int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C, int S,
-                    ActorActs& a, float* logits, float* probs, int32_t* argmax) {
+                    ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr) {
   const NetLayout& L = *cx.L;
   Arena& ar = *cx.ar;
   const int dff = L.dff, nl = L.nl;
@@ -294,6 +297,13 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
   a.w1d = ar.f((size_t)C * 128);
   a.score = ar.f((size_t)C * S);
   TPC_TRY(gemm_fwd(cx, y, 128, cx.W + L.w1p_t, 128, a.w1d, 128, C, 128, 128, epi_bias(cx.P + L.W1.b)));
+  if (fuse) {
+    fuse->w1d = a.w1d; fuse->kvw = a.dec[nl - 1].kvw; fuse->V = cx.P + L.V.w; fuse->bV = cx.P + L.V.b;
+    fuse->clipC = cx.m->dims.clip_C; fuse->has_clip = cx.m->dims.has_clip; fuse->ptr_mask = ptr_mask;
+    fuse->score = nullptr; fuse->logits = logits;
+    RUN(decide_step(*fuse, C, cx.st));
+    return TPC_OK;
+  }
   RUN(pointer_fwd(a.w1d, a.dec[nl - 1].kvw, cx.P + L.V.w, cx.P + L.V.b, cx.m->dims.clip_C, cx.m->dims.has_clip, ptr_mask,
                   C, S, a.score, logits, probs, argmax, cx.st));
   return TPC_OK;
@@ -357,9 +367,9 @@ int decoder_backward(Ctx& cx, const float* dec_input, int C, int S, ActorActs& a
 }
 
 int actor_forward(Ctx& cx, StateRef sr, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C,
-                  int N, int R, ActorActs& a, float* logits, float* probs, int32_t* argmax) {
+                  int N, int R, ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr) {
   TPC_TRY(encoder_forward(cx, sr, mha_mask, C, N, R, a.enc));
-  return decoder_forward(cx, dec_input, ptr_mask, mha_mask, C, N + R, a, logits, probs, argmax);
+  return decoder_forward(cx, dec_input, ptr_mask, mha_mask, C, N + R, a, logits, probs, argmax, fuse);
 }
 
 int actor_backward(Ctx& cx, StateRef sr, const float* dec_input, const float* mha_mask, int C, int N, int R,
@@ -493,45 +503,49 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
                  int64_t epoch, Arena& ar, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int S = N + R, T = R, F = e->num_features;
-  float* probs = ar.f((size_t)B * S);
-  int32_t* amax = reinterpret_cast<int32_t*>(ar.f(B));
-  float* rtmp = ar.f(B);
   float* dec_tmp = ar.f((size_t)B * F);
   float* mask_tmp = ar.f((size_t)B * S);
   const size_t mark = ar.off;
+  auto dec_at = [&](int t) { return buf->dec_inputs ? buf->dec_inputs + (size_t)t * B * F : dec_tmp; };
+  auto pmask_at = [&](int t) { return buf->ptr_masks ? buf->ptr_masks + (size_t)t * B * S : mask_tmp; };
+  if (!ar.dry) {
+    // inputs of step 0: decoder input = first rule, Agent.store copies (agents/trainer.py:68-76), feasible mask.
+    // For every later step the fused decision kernel of step t - 1 stages them.
+    gather_dec_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(buf->batch, B, S, F, N, dec_at(0));
+    TPC_CHECK_LAUNCH();
+    if (buf->states)
+      TPC_CHECK_CUDA(cudaMemcpyAsync(buf->states, buf->batch, (size_t)B * S * F * 4, cudaMemcpyDeviceToDevice, st));
+    if (buf->is_empties && buf->is_empty)
+      TPC_CHECK_CUDA(cudaMemcpyAsync(buf->is_empties, buf->is_empty, (size_t)B * S * 4, cudaMemcpyDeviceToDevice, st));
+    if (buf->mha_masks)
+      TPC_CHECK_CUDA(cudaMemcpyAsync(buf->mha_masks, buf->mha_mask, (size_t)B * S * 4, cudaMemcpyDeviceToDevice, st));
+    TPC_TRY(env_feasible_mask(*e, buf->batch, F, dec_at(0), buf->bin_net_mask, B, S, pmask_at(0), st));
+  }
   for (int t = 0; t < T; ++t) {
     ar.off = mark;
     Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, stream);
-    float* dec = buf->dec_inputs ? buf->dec_inputs + (size_t)t * B * F : dec_tmp;
-    float* pmask = buf->ptr_masks ? buf->ptr_masks + (size_t)t * B * S : mask_tmp;
-    const float* mha = buf->mha_mask;
-    int32_t* act = buf->actions + (size_t)t * B;
+    DecideArgs da{};
     if (!ar.dry) {
-      gather_dec_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(buf->batch, B, S, F, N + t, dec);
-      TPC_CHECK_LAUNCH();
-      // Agent.store copies (agents/trainer.py:68-76): state, mha mask (and is_empty) BEFORE the step
-      if (buf->states)
-        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->states + (size_t)t * B * S * F, buf->batch, (size_t)B * S * F * 4,
-                                       cudaMemcpyDeviceToDevice, st));
-      if (buf->is_empties && buf->is_empty)
-        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->is_empties + (size_t)t * B * S, buf->is_empty, (size_t)B * S * 4,
-                                       cudaMemcpyDeviceToDevice, st));
-      if (buf->mha_masks)
-        TPC_CHECK_CUDA(cudaMemcpyAsync(buf->mha_masks + (size_t)t * B * S, buf->mha_mask, (size_t)B * S * 4,
-                                       cudaMemcpyDeviceToDevice, st));
-      TPC_TRY(env_feasible_mask(*e, buf->batch, F, dec, buf->bin_net_mask, B, S, pmask, st));
+      da.greedy = greedy; da.seed = seed; da.id0 = id0; da.draw = epoch * T + t;
+      da.actions = buf->actions + (size_t)t * B;
+      da.env = *e;
+      da.batch = buf->batch; da.bin_mask = buf->bin_net_mask; da.mha_mask = buf->mha_mask; da.is_empty = buf->is_empty;
+      da.N = N; da.R = R; da.t = t;
+      da.rewards = buf->rewards;
+      if (t + 1 < T) {
+        da.dec_next = dec_at(t + 1);
+        da.pmask_next = pmask_at(t + 1);
+        da.states_next = buf->states ? buf->states + (size_t)(t + 1) * B * S * F : nullptr;
+        da.mha_next = buf->mha_masks ? buf->mha_masks + (size_t)(t + 1) * B * S : nullptr;
+        da.is_empties_next = (buf->is_empties && buf->is_empty) ? buf->is_empties + (size_t)(t + 1) * B * S : nullptr;
+      }
     }
     ActorActs a;
     StateRef sr{buf->batch, F, buf->is_empty};
-    TPC_TRY(actor_forward(cx, sr, dec, pmask, mha, B, N, R, a, buf->logits ? buf->logits + (size_t)t * B * S : nullptr,
-                          probs, greedy ? act : amax));
+    TPC_TRY(actor_forward(cx, sr, ar.dry ? nullptr : dec_at(t), ar.dry ? nullptr : pmask_at(t), buf->mha_mask, B, N, R, a,
+                          buf->logits ? buf->logits + (size_t)t * B * S : nullptr, nullptr, nullptr, &da));
     if (!ar.fits()) return TPC_ERR_WORKSPACE;
     if (ar.dry) break;
-    if (!greedy) TPC_TRY(sample_categorical(probs, B, S, seed, id0, epoch * T + t, act, st));
-    TPC_TRY(env_step(*e, buf->batch, buf->bin_net_mask, nullptr, buf->mha_mask, buf->is_empty, act, N + t, B, N, R, rtmp,
-                     st));
-    scatter_reward_kernel<<<ceil_div(B, 256), 256, 0, st>>>(rtmp, B, T, t, buf->rewards);
-    TPC_CHECK_LAUNCH();
   }
   return TPC_OK;
 }
