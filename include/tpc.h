@@ -235,6 +235,30 @@ int tpc_compare_solutions(tpc_handle* h, const float* net_dominant, const int32_
                           const float* heur_dominant, const int32_t* heur_rejected, int num_heuristics, int B,
                           float* net_dominant_rounded, int32_t* results, void* stream);
 
+/* KnapsackV2 tester (environment/custom/knapsack_v2/tester.py, heuristic/*, misc/utils.py:41-95). state rows: bins
+ * (capacity, current_load) with row 0 = EOS bin, then items (weight, value). assign (B, num_items) int32 = bin per
+ * item (0 = rejected), order (B, num_items) = item placed k-th, bins (B, num_bins, 2) = (capacity, load) afterwards,
+ * values (B, num_bins) = Bin.current_value (fp32 sums in placement order). */
+/* replaces WasteReductionHeuristic.solve (heuristic/waste_reduction.py:26-72, bin.py:34-60, item.py:14) */
+int tpc_knapsack_waste_reduction(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                                 int num_items, int item_sort_descending, int bin_sort_descending, int32_t* assign,
+                                 int32_t* order, float* bins, float* values, void* stream);
+/* replaces RandomHeuristic.solve (knapsack_v2/heuristic/random_heuristic.py:24-52); draws as tpc_heuristic_random */
+int tpc_knapsack_random(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                        int num_items, uint64_t seed, int64_t instance_id0, int64_t epoch, int32_t* assign,
+                        int32_t* order, float* bins, float* values, void* stream);
+/* Bin.current_value per bin for a placement made in item order (the net's history, knapsack_v2/env.py); assign is
+ * read as assign[b * stride_instance + j * stride_item]; item values come from state */
+int tpc_knapsack_bin_values(tpc_handle* h, const int32_t* assign, int64_t stride_instance, int64_t stride_item,
+                            const float* state, int ld_instance, int ld_row, int B, int num_bins, int num_items,
+                            float* values, void* stream);
+/* replaces compute_stats (knapsack_v2/misc/utils.py:41-58): reward = sum of the real bins' values, empty bins,
+ * rejected items, value collected by the EOS bin. The won / draw / lost verdict (misc/utils.py:60-95) is
+ * tpc_compare_solutions with the rewards in the `dominant` slots. */
+int tpc_knapsack_stats(tpc_handle* h, const int32_t* assign, int64_t stride_instance, int64_t stride_item,
+                       const float* values, int B, int num_bins, int num_items, float* reward, int32_t* empty_bins,
+                       int32_t* rejected, float* rejected_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,3 +123,83 @@ def compare_solutions(net_dominant, net_rejected, heur_dominant, heur_rejected):
     cd = 2 if max_dom > nd else (1 if max_dom == nd else 0)
     cr = 2 if min_rej < net_rejected else (1 if min_rej == net_rejected else 0)
     return nd, cd, cr
+
+
+# ---- KnapsackV2 (environment/custom/knapsack_v2/heuristic/*, bin.py, item.py, misc/utils.py:41-58) ---------------
+# state (S, 2): bin rows (capacity, current_load), row 0 = EOS bin; item rows (weight, value).
+def _kn_remaining(cap, load, w):
+    """Bin.compute_remaining_capacity (bin.py:44-47): rhu(capacity - rhu(load + weight))."""
+    return rhu2(F32(cap) - rhu2(F32(load) + F32(w)))
+
+
+def _kn_insert(bins, values, n, item):
+    """Bin.insert_item (bin.py:49-60): bin 0 (EOS) only collects the value."""
+    if n != 0:
+        bins[n, 1] = rhu2(bins[n, 1] + item[0])
+    values[n] = F32(values[n] + item[1])
+
+
+def knapsack_waste_reduction(state, num_bins, item_sort_descending, bin_sort_descending):
+    """WasteReductionHeuristic.solve (waste_reduction.py:26-72). Returns (assign (R,), order (R,) = placement order,
+    bins (num_bins, 2) after the placement, values (num_bins,) = Bin.current_value)."""
+    state = np.asarray(state, dtype=F32)
+    bins, items = state[:num_bins].copy(), state[num_bins:]
+    values = np.zeros(num_bins, dtype=F32)
+    ratio = (items[:, 1] / items[:, 0]).astype(F32)                       # Item.ratio (item.py:14)
+    order = sorted(range(len(items)), key=lambda j: ratio[j], reverse=bool(item_sort_descending))
+    assign = np.zeros(len(items), dtype=np.int32)
+    for j in order:
+        diffs = [_kn_remaining(bins[n, 0], bins[n, 1], items[j, 0]) for n in range(1, num_bins)]
+        cand = sorted(range(len(diffs)), key=lambda n: diffs[n], reverse=bool(bin_sort_descending))
+        pick = 0
+        for n in cand:
+            if diffs[n] >= 0:
+                pick = 1 + n
+                break
+        _kn_insert(bins, values, pick, items[j])
+        assign[j] = pick
+    return assign, np.asarray(order, dtype=np.int32), bins, values
+
+
+def knapsack_random(state, num_bins, randrange):
+    """RandomHeuristic.solve (knapsack_v2/heuristic/random_heuristic.py:24-52)."""
+    state = np.asarray(state, dtype=F32)
+    bins, items = state[:num_bins].copy(), state[num_bins:]
+    values = np.zeros(num_bins, dtype=F32)
+    left = list(range(len(items)))
+    assign = np.zeros(len(items), dtype=np.int32)
+    order = []
+    while left:
+        j = left.pop(randrange(len(left)))
+        cand = list(range(1, num_bins))
+        pick = 0
+        while cand:
+            n = cand.pop(randrange(len(cand)))
+            if _kn_remaining(bins[n, 0], bins[n, 1], items[j, 0]) >= 0:      # Bin.can_fit_item (bin.py:40-42)
+                pick = n
+                break
+        _kn_insert(bins, values, pick, items[j])
+        assign[j] = pick
+        order.append(j)
+    return assign, np.asarray(order, dtype=np.int32), bins, values
+
+
+def knapsack_bin_values(assign, state, num_bins, order=None):
+    """Bin.current_value of every bin when the items are inserted in `order` (default: item order = the net's
+    decoding order): sequential fp32 sums."""
+    items = np.asarray(state, dtype=F32)[num_bins:]
+    values = np.zeros(num_bins, dtype=F32)
+    for j in (range(len(items)) if order is None else order):
+        values[assign[j]] = F32(values[assign[j]] + items[j, 1])
+    return values
+
+
+def knapsack_solution_stats(assign, values):
+    """compute_stats (knapsack_v2/misc/utils.py:41-58): (reward, empty bins, rejected items, rejected value)."""
+    num_bins = len(values)
+    reward = F32(0)
+    for n in range(1, num_bins):
+        reward = F32(reward + values[n])
+    used = np.zeros(num_bins, dtype=bool)
+    used[assign] = True
+    return reward, int((~used[1:]).sum()), int((np.asarray(assign) == 0).sum()), F32(values[0])

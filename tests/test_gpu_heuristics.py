@@ -167,3 +167,123 @@ def test_net_stats_and_tester_sweep_full_batch(tmp_path):
     best_rej = np.min([list(s.values())[1] for s in stats[1:]], axis=0)
     net_rej = stats[0]["net_rejected"]
     assert rres[2] >= 0 and (best_rej <= 100).all() and (net_rej <= 100).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KnapsackV2
+# ---------------------------------------------------------------------------------------------------------------
+KG = np.load(os.path.join(os.path.dirname(__file__), "golden", "heuristic_knapsack_v2.npz"))
+
+
+def _kn_instances(rng, B, n_bins, n_items, lo, hi):
+    s = np.zeros((B, n_bins + n_items, 2), dtype=np.float32)
+    s[:, 0] = -2
+    s[:, 1:n_bins, 0] = (rng.integers(lo, hi, size=(B, n_bins - 1)) / 100).astype(np.float32)
+    s[:, n_bins:, 0] = (rng.integers(1, 30, size=(B, n_items)) / 100).astype(np.float32)
+    s[:, n_bins:, 1] = (rng.integers(1, 100, size=(B, n_items)) / 100).astype(np.float32)
+    return s
+
+
+def test_knapsack_waste_reduction_equals_reference_placements():
+    from tpc_b200.heuristics import WasteReductionHeuristic
+    groups = {}
+    for i in range(int(KG["num_cases"])):
+        groups.setdefault((int(KG[f"c{i}_bins"]), KG[f"c{i}_state"].shape[0]), []).append(i)
+    for (n_bins, _), idxs in groups.items():
+        batch = np.stack([KG[f"c{i}_state"] for i in idxs])
+        for i_desc in (1, 0):
+            for b_desc in (1, 0):
+                sol = WasteReductionHeuristic(n_bins, {"item_sort_descending": bool(i_desc),
+                                                       "bin_sort_descending": bool(b_desc)}, DEV)
+                sol.solve(batch)
+                s = sol.solution
+                rw, emp, rej, rv = (t.cpu().numpy() for t in sol.stats())
+                for k, i in enumerate(idxs):
+                    tag = f"c{i}_wr_{i_desc}{b_desc}"
+                    np.testing.assert_array_equal(s.assign.cpu().numpy()[k], KG[tag + "_assign"])
+                    np.testing.assert_array_equal(s.bins.cpu().numpy()[k, 1:], KG[tag + "_bins"][1:])
+                    np.testing.assert_array_equal(s.values.cpu().numpy()[k], KG[tag + "_values"])
+                    ref = KG[tag + "_stats"]
+                    assert (float(rw[k]), int(emp[k]), int(rej[k]), float(rv[k])) == \
+                        (float(np.float32(ref[0])), int(ref[1]), int(ref[2]), float(np.float32(ref[3])))
+    assert sol.name == "item_ASC_False_bin_ASC_False"
+
+
+@pytest.mark.parametrize("shape", [(40, 6, 10, 10, 100), (24, 11, 20, 10, 40), (16, 51, 100, 10, 100), (7, 2, 3, 5, 60)])
+def test_knapsack_heuristics_equal_oracle(shape):
+    import torch
+    from tpc_b200.heuristics import knapsack_heuristic_factory, knapsack_stats
+    from tpc_b200 import lib as L
+    from tpc_b200.heuristics import _handle, _stream
+    B, n_bins, n_items, lo, hi = shape
+    batch = _kn_instances(np.random.default_rng(sum(shape)), B, n_bins, n_items, lo, hi)
+    opts = {"waste_reduction": {"generate_params_combos": True, "item_sort_descending": True,
+                                "bin_sort_descending": False}, "random": {}, "or_tools": {}}
+    solvers = knapsack_heuristic_factory(n_bins, opts, DEV, seed=7, instance_id0=500)
+    assert [s.name for s in solvers] == [f"item_ASC_{i}_bin_ASC_{b}" for i in (True, False) for b in (True, False)] + ["random"]
+    for rep in range(2):
+        for s in solvers:
+            s.solve(batch)
+        for s in solvers:
+            sol = s.solution
+            a, o, bn, vl = (t.cpu().numpy() for t in (sol.assign, sol.order, sol.bins, sol.values))
+            rw, emp, rej, rv = (t.cpu().numpy() for t in s.stats())
+            for b in range(B):
+                if s.name == "random":
+                    oa, oo, ob, ov = oh.knapsack_random(batch[b], n_bins, oh.philox_randrange(7, 500 + b, rep))
+                else:
+                    oa, oo, ob, ov = oh.knapsack_waste_reduction(batch[b], n_bins, s.item_sort_descending,
+                                                                 s.bin_sort_descending)
+                np.testing.assert_array_equal(a[b], oa)
+                np.testing.assert_array_equal(o[b], oo)
+                np.testing.assert_array_equal(bn[b, 1:], ob[1:])
+                np.testing.assert_array_equal(vl[b], ov)
+                assert (rw[b], emp[b], rej[b], rv[b]) == oh.knapsack_solution_stats(oa, ov)
+    # per-bin values of a placement made in item order (the net's history): step-major actions (T, B)
+    acts = torch.as_tensor(np.random.default_rng(1).integers(0, n_bins, size=(n_items, B)).astype(np.int32)).to(DEV)
+    st = torch.as_tensor(batch).to(DEV)
+    lib, h = _handle(torch.device(DEV))
+    values = torch.empty(B, n_bins, dtype=torch.float32, device=DEV)
+    L.check(lib.tpc_knapsack_bin_values(h, L.ptr(acts), 1, acts.stride(0), L.ptr(st), st.stride(0), st.stride(1), B,
+                                        n_bins, n_items, L.ptr(values), _stream(torch.device(DEV))))
+    rw, emp, rej, rv = (t.cpu().numpy() for t in knapsack_stats(acts, 1, acts.stride(0), values))
+    for b in range(B):
+        ov = oh.knapsack_bin_values(acts[:, b].cpu().numpy(), batch[b], n_bins)
+        np.testing.assert_array_equal(values[b].cpu().numpy(), ov)
+        assert (rw[b], emp[b], rej[b], rv[b]) == oh.knapsack_solution_stats(acts[:, b].cpu().numpy(), ov)
+
+
+def test_knapsack_tester_sweep(tmp_path):
+    """configs/KnapsackV2.json test bed (reduced), batch 64: verdict counts, CSV layout, reward == episode return."""
+    import torch
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import env_factory
+    agent_cfg, _, env_cfg, tester_cfg, _, _ = get_configs("KnapsackV2", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=64)
+    env, tester = env_factory("custom", "KnapsackV2", env_cfg, DEV)
+    env.add_stats_to_agent_config(agent_cfg)
+    agent = Agent("transformer", agent_cfg, DEV, num_features=2, seed=9)
+    tcfg = json.loads(json.dumps(tester_cfg))
+    tcfg.update(batch_size=64)
+    tcfg["testbed"].update(num_tests=1, bin_sample_configs={"min": 5, "max": 10, "step": 5},
+                           item_sample_configs={"min": 10, "max": 20, "step": 10})
+    res = tester(env, agent, tcfg, str(tmp_path))
+    assert res.shape == (3,) and res.sum() == 4 * 64
+    lines = open(os.path.join(str(tmp_path), "tests", "test.csv")).read().splitlines()
+    assert lines[0].startswith("test_instance;bin_sample_size;bin_min_value;bin_max_value;item_sample_size;"
+                               "net reward;net empty bins;net num rejected items;net rejected value;"
+                               "item ASC True bin ASC True reward;")
+    assert len(lines) == 1 + 4 * 64 and all(len(l.split(";")) == 5 + 6 * 4 + 1 for l in lines)
+    # the net's reward statistic equals the sum of the environment's step rewards (value of every placed item)
+    env.set_testing_mode(64, 10, 20, 0, 100)
+    agent.set_testing_mode(64, env.node_sample_size, env.profiles_sample_size)
+    from tpc_b200.heuristics import knapsack_net_stats
+    bufs = env.device_buffers(store=False)
+    env.reset_into(bufs)
+    init = bufs.batch.clone()
+    agent.rollout(env, bufs, greedy=True)
+    (rw, _, rej, rv), values = knapsack_net_stats(bufs, init, env.node_sample_size)
+    total = bufs.rewards.sum(dim=1)
+    assert torch.allclose(rw, total, atol=1e-5) and torch.all((rej == 0) == (rv == 0))

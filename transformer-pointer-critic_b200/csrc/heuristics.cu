@@ -215,6 +215,197 @@ __global__ void compare_kernel(const float* __restrict__ net_dom, const int32_t*
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// KnapsackV2 (environment/custom/knapsack_v2/heuristic/{waste_reduction,random_heuristic}.py, bin.py:34-60, item.py,
+// misc/utils.py:41-58). state rows: bins (capacity, current_load), items (weight, value).
+// shared memory of one warp: cap[N] | load[N] | val[N] | w[R] | v[R] | list_a[R] | list_b[N]
+// ------------------------------------------------------------------------------------------------------------------
+struct KnSmem {
+  float *cap, *load, *val, *w, *v;
+  int *la, *lb;
+};
+__device__ __forceinline__ KnSmem kn_carve(float* base, int N, int R) {
+  KnSmem k;
+  k.cap = base; k.load = k.cap + N; k.val = k.load + N; k.w = k.val + N; k.v = k.w + R;
+  k.la = reinterpret_cast<int*>(k.v + R); k.lb = k.la + R;
+  return k;
+}
+__host__ __device__ inline int kn_floats(int N, int R) { return 4 * N + 3 * R; }
+
+__device__ __forceinline__ void kn_load(const float* __restrict__ inst, int ld_row, int N, int R, const KnSmem& k, int lane) {
+  for (int n = lane; n < N; n += 32) {
+    k.cap[n] = inst[(size_t)n * ld_row];
+    k.load[n] = inst[(size_t)n * ld_row + 1];
+    k.val[n] = 0.f;
+  }
+  for (int j = lane; j < R; j += 32) {
+    k.w[j] = inst[(size_t)(N + j) * ld_row];
+    k.v[j] = inst[(size_t)(N + j) * ld_row + 1];
+  }
+  __syncwarp();
+}
+// Bin.compute_remaining_capacity (bin.py:44-47)
+__device__ __forceinline__ float kn_remaining(float cap, float load, float w) {
+  return rhu2(__fsub_rn(cap, rhu2(__fadd_rn(load, w))));
+}
+// Bin.insert_item (bin.py:49-60) by lane 0; bin 0 (EOS) only collects the value
+__device__ __forceinline__ void kn_insert(const KnSmem& k, int n, int j) {
+  if (n != 0) k.load[n] = rhu2(__fadd_rn(k.load[n], k.w[j]));
+  k.val[n] = __fadd_rn(k.val[n], k.v[j]);
+}
+__device__ __forceinline__ void kn_store(const KnSmem& k, int N, float* __restrict__ bins_out, float* __restrict__ values_out,
+                                         int lane) {
+  for (int n = lane; n < N; n += 32) {
+    bins_out[2 * n] = k.cap[n];
+    bins_out[2 * n + 1] = k.load[n];
+    values_out[n] = k.val[n];
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+knapsack_wr_kernel(const float* __restrict__ state, int ld_inst, int ld_row, int B, int N, int R, int item_desc,
+                   int bin_desc, int32_t* __restrict__ assign, int32_t* __restrict__ order_out,
+                   float* __restrict__ bins_out, float* __restrict__ values_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  if (b >= B) return;
+  const KnSmem k = kn_carve(smem + (size_t)warp * kn_floats(N, R), N, R);
+  kn_load(state + (size_t)b * ld_inst, ld_row, N, R, k, lane);
+  // sorted(item_list, key=value / weight, reverse=item_desc), stable (waste_reduction.py:36-40, item.py:14)
+  for (int j = lane; j < R; j += 32) {
+    const float kj = __fdiv_rn(k.v[j], k.w[j]);
+    int pos = 0;
+    for (int i = 0; i < R; ++i) {
+      const float ki = __fdiv_rn(k.v[i], k.w[i]);
+      pos += (item_desc ? ki > kj : ki < kj) || (ki == kj && i < j);
+    }
+    k.la[pos] = j;
+  }
+  __syncwarp();
+  for (int t = 0; t < R; ++t) {
+    const int j = k.la[t];
+    const float w = k.w[j];
+    float best = 0.f;
+    int best_n = 0;
+    for (int n = 1 + lane; n < N; n += 32) {
+      const float d = kn_remaining(k.cap[n], k.load[n], w);
+      if (d >= 0.f && (best_n == 0 || (bin_desc ? d > best : d < best))) {
+        best = d;
+        best_n = n;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
+      const bool take = on != 0 && (best_n == 0 || (bin_desc ? ob > best : ob < best) || (ob == best && on < best_n));
+      if (take) {
+        best = ob;
+        best_n = on;
+      }
+    }
+    if (lane == 0) {
+      kn_insert(k, best_n, j);
+      assign[(size_t)b * R + j] = best_n;
+      order_out[(size_t)b * R + t] = j;
+    }
+    __syncwarp();
+  }
+  kn_store(k, N, bins_out + (size_t)b * N * 2, values_out + (size_t)b * N, lane);
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+knapsack_random_kernel(const float* __restrict__ state, int ld_inst, int ld_row, int B, int N, int R, uint64_t seed,
+                       int64_t id0, int64_t epoch, int32_t* __restrict__ assign, int32_t* __restrict__ order_out,
+                       float* __restrict__ bins_out, float* __restrict__ values_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  if (b >= B) return;
+  const KnSmem k = kn_carve(smem + (size_t)warp * kn_floats(N, R), N, R);
+  kn_load(state + (size_t)b * ld_inst, ld_row, N, R, k, lane);
+  for (int j = lane; j < R; j += 32) k.la[j] = j;
+  __syncwarp();
+  Stream s = make_stream(seed, id0 + b, epoch, 4);
+  uint32_t draw = 0;
+  for (int n_left = R; n_left > 0; --n_left) {
+    const int j = list_pop(k.la, n_left, (int)__umulhi(s.draw(draw++), (uint32_t)n_left), lane);
+    for (int n = lane; n < N - 1; n += 32) k.lb[n] = n + 1;
+    __syncwarp();
+    int placed = 0;
+    for (int n_bins = N - 1; n_bins > 0; --n_bins) {
+      const int n = list_pop(k.lb, n_bins, (int)__umulhi(s.draw(draw++), (uint32_t)n_bins), lane);
+      if (kn_remaining(k.cap[n], k.load[n], k.w[j]) >= 0.f) {   // Bin.can_fit_item (bin.py:40-42)
+        placed = n;
+        break;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      kn_insert(k, placed, j);
+      assign[(size_t)b * R + j] = placed;
+      order_out[(size_t)b * R + (R - n_left)] = j;
+    }
+    __syncwarp();
+  }
+  kn_store(k, N, bins_out + (size_t)b * N * 2, values_out + (size_t)b * N, lane);
+}
+
+// Bin.current_value of every bin for a placement made in item order (the net's decoding order): lane = bin, items
+// scanned in order, so every bin's fp32 sum has the reference's operation sequence.
+__global__ void __launch_bounds__(WARPS * 32)
+knapsack_bin_values_kernel(const int32_t* __restrict__ assign, long long sa_inst, long long sa_item,
+                           const float* __restrict__ state, int ld_inst, int ld_row, int B, int N, int R,
+                           float* __restrict__ values_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  if (b >= B) return;
+  const float* inst = state + (size_t)b * ld_inst;
+  for (int n = lane; n < N; n += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < R; ++j)
+      if (assign[(size_t)b * sa_inst + (size_t)j * sa_item] == n) acc = __fadd_rn(acc, inst[(size_t)(N + j) * ld_row + 1]);
+    values_out[(size_t)b * N + n] = acc;
+  }
+}
+
+// compute_stats (knapsack_v2/misc/utils.py:41-58)
+__global__ void __launch_bounds__(WARPS * 32)
+knapsack_stats_kernel(const int32_t* __restrict__ assign, long long sa_inst, long long sa_item,
+                      const float* __restrict__ values, int B, int N, int R, float* __restrict__ reward,
+                      int32_t* __restrict__ empty_bins, int32_t* __restrict__ rejected, float* __restrict__ rejected_value) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  if (b >= B) return;
+  int* used = reinterpret_cast<int*>(smem) + (size_t)warp * N;
+  for (int n = lane; n < N; n += 32) used[n] = 0;
+  __syncwarp();
+  int rej = 0;
+  for (int j = lane; j < R; j += 32) {
+    const int a = assign[(size_t)b * sa_inst + (size_t)j * sa_item];
+    rej += a == 0;
+    if (a >= 0 && a < N) used[a] = 1;
+  }
+  __syncwarp();
+  int empty = 0;
+  for (int n = 1 + lane; n < N; n += 32) empty += used[n] == 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    empty += __shfl_xor_sync(0xffffffffu, empty, o);
+    rej += __shfl_xor_sync(0xffffffffu, rej, o);
+  }
+  if (lane == 0) {
+    float r = 0.f;   // reward = 0; reward += node.current_value, bins in order
+    for (int n = 1; n < N; ++n) r = __fadd_rn(r, values[(size_t)b * N + n]);
+    reward[b] = r;
+    empty_bins[b] = empty;
+    rejected[b] = rej;
+    rejected_value[b] = values[(size_t)b * N];
+  }
+}
+
 int check_shape(int B, int N, int R, size_t smem_bytes) {
   if (B < 0 || N < 2 || R < 1) return TPC_ERR_SHAPE;
   if (smem_bytes > 200 * 1024) return TPC_ERR_SHAPE;
@@ -289,6 +480,61 @@ int tpc_compare_solutions(tpc_handle* h, const float* net_dominant, const int32_
   compare_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(net_dominant, net_rejected, heur_dominant,
                                                                       heur_rejected, num_heuristics, B,
                                                                       net_dominant_rounded, results);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_knapsack_waste_reduction(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                                 int num_items, int item_sort_descending, int bin_sort_descending, int32_t* assign,
+                                 int32_t* order, float* bins, float* values, void* stream) {
+  if (!h || !state || !assign || !order || !bins || !values) return TPC_ERR_ARG;
+  const size_t smem = (size_t)WARPS * kn_floats(num_bins, num_items) * sizeof(float);
+  TPC_TRY(check_shape(B, num_bins, num_items, smem));
+  if (B == 0) return TPC_OK;
+  TPC_TRY(opt_in_smem(knapsack_wr_kernel, smem));
+  knapsack_wr_kernel<<<ceil_div(B, WARPS), WARPS * 32, smem, (cudaStream_t)stream>>>(
+      state, ld_instance, ld_row, B, num_bins, num_items, item_sort_descending != 0, bin_sort_descending != 0, assign,
+      order, bins, values);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_knapsack_random(tpc_handle* h, const float* state, int ld_instance, int ld_row, int B, int num_bins,
+                        int num_items, uint64_t seed, int64_t instance_id0, int64_t epoch, int32_t* assign,
+                        int32_t* order, float* bins, float* values, void* stream) {
+  if (!h || !state || !assign || !order || !bins || !values) return TPC_ERR_ARG;
+  const size_t smem = (size_t)WARPS * kn_floats(num_bins, num_items) * sizeof(float);
+  TPC_TRY(check_shape(B, num_bins, num_items, smem));
+  if (B == 0) return TPC_OK;
+  TPC_TRY(opt_in_smem(knapsack_random_kernel, smem));
+  knapsack_random_kernel<<<ceil_div(B, WARPS), WARPS * 32, smem, (cudaStream_t)stream>>>(
+      state, ld_instance, ld_row, B, num_bins, num_items, seed, instance_id0, epoch, assign, order, bins, values);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_knapsack_bin_values(tpc_handle* h, const int32_t* assign, int64_t stride_instance, int64_t stride_item,
+                            const float* state, int ld_instance, int ld_row, int B, int num_bins, int num_items,
+                            float* values, void* stream) {
+  if (!h || !assign || !state || !values) return TPC_ERR_ARG;
+  TPC_TRY(check_shape(B, num_bins, num_items, 0));
+  if (B == 0) return TPC_OK;
+  knapsack_bin_values_kernel<<<ceil_div(B, WARPS), WARPS * 32, 0, (cudaStream_t)stream>>>(
+      assign, stride_instance, stride_item, state, ld_instance, ld_row, B, num_bins, num_items, values);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_knapsack_stats(tpc_handle* h, const int32_t* assign, int64_t stride_instance, int64_t stride_item,
+                       const float* values, int B, int num_bins, int num_items, float* reward, int32_t* empty_bins,
+                       int32_t* rejected, float* rejected_value, void* stream) {
+  if (!h || !assign || !values || !reward || !empty_bins || !rejected || !rejected_value) return TPC_ERR_ARG;
+  const size_t smem = (size_t)WARPS * num_bins * sizeof(int);
+  TPC_TRY(check_shape(B, num_bins, num_items, smem));
+  if (B == 0) return TPC_OK;
+  TPC_TRY(opt_in_smem(knapsack_stats_kernel, smem));
+  knapsack_stats_kernel<<<ceil_div(B, WARPS), WARPS * 32, smem, (cudaStream_t)stream>>>(
+      assign, stride_instance, stride_item, values, B, num_bins, num_items, reward, empty_bins, rejected, rejected_value);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

@@ -255,9 +255,14 @@ class KnapsackEnvironmentV2(_DeviceEnvBase):
         agent_config["encoder_embedding"] = {"common": False, "num_bin_features": 2, "num_resource_features": 2}
         return agent_config
 
-    def set_testing_mode(self, batch_size, bin_sample_size, item_sample_size, *_):
+    def set_testing_mode(self, batch_size, bin_sample_size, item_sample_size, bin_min_capacity=None,
+                         bin_max_capacity=None):
+        """knapsack_v2/env.py:334-352."""
         self.gather_stats = True
         self.batch_size = batch_size
+        if bin_min_capacity is not None and bin_max_capacity is not None:
+            self.bin_min_capacity, self.bin_max_capacity = bin_min_capacity, bin_max_capacity
+            self._cfg.node_min_val, self._cfg.node_max_val = bin_min_capacity, bin_max_capacity
         self.bin_sample_size = self.node_sample_size = bin_sample_size + 1
         self.item_sample_size = self.profiles_sample_size = item_sample_size
 

@@ -194,3 +194,122 @@ def compare_solutions(net_dominant, net_rejected, heur_dominant, heur_rejected):
     L.check(lib.tpc_compare_solutions(h, L.ptr(net_dominant), L.ptr(net_rejected), L.ptr(hd), L.ptr(hr), H, B,
                                       L.ptr(rounded), L.ptr(results), _stream(device)), "tpc_compare_solutions")
     return rounded, results
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KnapsackV2 (environment/custom/knapsack_v2/heuristic/*, misc/utils.py:41-95)
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class KnapsackSolution:
+    assign: torch.Tensor      # (B, R) int32: bin per item, 0 = rejected
+    order: torch.Tensor       # (B, R) int32: item placed k-th
+    bins: torch.Tensor        # (B, N, 2) fp32 (capacity, load)
+    values: torch.Tensor      # (B, N) fp32 Bin.current_value
+
+
+class _KnapsackBase(BaseHeuristic):
+    """knapsack_v2/heuristic/base_heuristic.py (num_bins instead of num_nodes, no normalization factor)."""
+
+    def __init__(self, num_bins: int, device="cuda:0"):
+        super().__init__(num_bins, 1, device)
+        self.num_bins = num_bins
+
+    def _state(self, state):
+        t = state if torch.is_tensor(state) else torch.as_tensor(np.asarray(state, dtype=np.float32))
+        t = t.to(device=self.device, dtype=torch.float32)
+        if t.dim() != 3 or t.shape[2] < 2 or t.shape[1] <= self.num_bins:
+            raise ValueError(f"state must be (batch, bins + items, >= 2 features), got {tuple(t.shape)}")
+        return t.contiguous()
+
+    def _alloc(self, st):
+        B, R = st.shape[0], st.shape[1] - self.num_bins
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=self.device)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        return B, R, KnapsackSolution(i32(B, R), i32(B, R), f32(B, self.num_bins, 2), f32(B, self.num_bins))
+
+    def stats(self):
+        """compute_stats (knapsack_v2/misc/utils.py:41-58): (reward, empty bins, rejected items, rejected value)."""
+        sol = self.solution
+        return knapsack_stats(sol.assign, sol.assign.stride(0), sol.assign.stride(1), sol.values)
+
+
+class WasteReductionHeuristic(_KnapsackBase):
+    """knapsack_v2/heuristic/waste_reduction.py:13-72."""
+
+    def __init__(self, num_bins: int, opts: dict, device="cuda:0"):
+        super().__init__(num_bins, device)
+        self.item_sort_descending = opts["item_sort_descending"]
+        self.bin_sort_descending = opts["bin_sort_descending"]
+        self.name = f"item_ASC_{self.item_sort_descending}_bin_ASC_{self.bin_sort_descending}"
+
+    def solve(self, state):
+        st = self._state(state)
+        lib, h = _handle(self.device)
+        B, R, sol = self._alloc(st)
+        L.check(lib.tpc_knapsack_waste_reduction(h, L.ptr(st), st.stride(0), st.stride(1), B, self.num_bins, R,
+                                                 1 if self.item_sort_descending else 0,
+                                                 1 if self.bin_sort_descending else 0, L.ptr(sol.assign),
+                                                 L.ptr(sol.order), L.ptr(sol.bins), L.ptr(sol.values),
+                                                 _stream(self.device)), "tpc_knapsack_waste_reduction")
+        self.resource_batch_id += 1
+        self.solution = sol
+
+
+class KnapsackRandomHeuristic(_KnapsackBase):
+    """knapsack_v2/heuristic/random_heuristic.py:13-52 (Philox stream per instance, see RandomHeuristic)."""
+
+    def __init__(self, num_bins: int, opts: dict, device="cuda:0", seed: int = 1235, instance_id0: int = 0):
+        super().__init__(num_bins, device)
+        self.seed, self.instance_id0 = int(seed), int(instance_id0)
+        self.name = "random"
+
+    def solve(self, state):
+        st = self._state(state)
+        lib, h = _handle(self.device)
+        B, R, sol = self._alloc(st)
+        L.check(lib.tpc_knapsack_random(h, L.ptr(st), st.stride(0), st.stride(1), B, self.num_bins, R, self.seed,
+                                        self.instance_id0, self.resource_batch_id, L.ptr(sol.assign), L.ptr(sol.order),
+                                        L.ptr(sol.bins), L.ptr(sol.values), _stream(self.device)), "tpc_knapsack_random")
+        self.resource_batch_id += 1
+        self.solution = sol
+
+
+def knapsack_heuristic_factory(num_bins: int, opts: dict, device="cuda:0", seed: int = 1235, instance_id0: int = 0):
+    """knapsack_v2/heuristic/factory.py:5-50: waste-reduction combos, random. The reference also appends an ORTools
+    solver (heuristic/or_tools.py); Google OR-Tools is not installable here, so it is left out."""
+    wr = opts["waste_reduction"]
+    if wr["generate_params_combos"]:
+        solvers = [WasteReductionHeuristic(num_bins, {"item_sort_descending": i, "bin_sort_descending": b}, device)
+                   for i in (True, False) for b in (True, False)]
+    else:
+        solvers = [WasteReductionHeuristic(num_bins, wr, device)]
+    return solvers + [KnapsackRandomHeuristic(num_bins, opts["random"], device, seed, instance_id0)]
+
+
+def knapsack_stats(assign, stride_instance, stride_item, values):
+    device = values.device
+    lib, h = _handle(device)
+    B, N = values.shape
+    R = assign.numel() // B
+    reward = torch.empty(B, dtype=torch.float32, device=device)
+    empty = torch.empty(B, dtype=torch.int32, device=device)
+    rejected = torch.empty(B, dtype=torch.int32, device=device)
+    rej_value = torch.empty(B, dtype=torch.float32, device=device)
+    L.check(lib.tpc_knapsack_stats(h, L.ptr(assign), stride_instance, stride_item, L.ptr(values), B, N, R,
+                                   L.ptr(reward), L.ptr(empty), L.ptr(rejected), L.ptr(rej_value), _stream(device)),
+            "tpc_knapsack_stats")
+    return reward, empty, rejected, rej_value
+
+
+def knapsack_net_stats(bufs, initial_state: torch.Tensor, num_bins: int):
+    """compute_stats of the net's placement: per-bin values summed in decoding order (what env.history holds in the
+    reference), then the same statistics as the heuristics."""
+    device = initial_state.device
+    lib, h = _handle(device)
+    B, R = bufs.actions.shape[1], bufs.actions.shape[0]
+    st = initial_state.contiguous()
+    values = torch.empty(B, num_bins, dtype=torch.float32, device=device)
+    L.check(lib.tpc_knapsack_bin_values(h, L.ptr(bufs.actions), 1, bufs.actions.stride(0), L.ptr(st), st.stride(0),
+                                        st.stride(1), B, num_bins, R, L.ptr(values), _stream(device)),
+            "tpc_knapsack_bin_values")
+    return knapsack_stats(bufs.actions, 1, bufs.actions.stride(0), values), values

@@ -91,6 +91,14 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "tpc_compare_solutions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
+    "tpc_knapsack_waste_reduction": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tpc_knapsack_random": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_i64, c_i64, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tpc_knapsack_bin_values": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "tpc_knapsack_stats": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -130,22 +130,78 @@ def test(env, agent, opts: dict, log_dir: str):
     return dominant_results, rejected_results
 
 
+def knapsack_test_single_instance(instance_id, env, agent, opts: dict, batch_size: int, bin_sample_size: int,
+                                  bin_min_val: int, bin_max_val: int, item_sample_size: int, log_dir: str):
+    """knapsack_v2/tester.py:101-233 -> (stats, reward_result[3]); statistics for every instance of the batch."""
+    from .heuristics import knapsack_heuristic_factory, knapsack_net_stats
+    env.set_testing_mode(batch_size, bin_sample_size, item_sample_size, bin_min_val, bin_max_val)
+    agent.set_testing_mode(batch_size, env.node_sample_size, env.profiles_sample_size)
+    N = env.node_sample_size
+    bufs = env.device_buffers(store=False)
+    env.reset_into(bufs)
+    solvers = knapsack_heuristic_factory(N, opts["heuristic"], env.device, seed=env.seed_value,
+                                         instance_id0=env.episode_id0)
+    heuristic_input_state = bufs.batch.clone()
+    agent.rollout(env, bufs, greedy=True)
+    for solver in solvers:
+        solver.solve(heuristic_input_state)
+    (net_reward, net_empty, net_rej, net_rej_value), _ = knapsack_net_stats(bufs, heuristic_input_state, N)
+    h_stats = [s.stats() for s in solvers]
+    # gather_stats_from_solutions (knapsack_v2/misc/utils.py:60-95): rounded rewards, heuristics start from -1
+    dummy = torch.zeros_like(net_rej)
+    net_rounded, results = compare_solutions(net_reward, dummy, [h[0] for h in h_stats], [dummy for _ in h_stats])
+    host = lambda t: t.cpu().numpy()
+    stats = [{"net_reward": host(net_rounded), "net_empty_bins": host(net_empty),
+              "net_num_rejected_items": host(net_rej), "net_rejected_value": host(net_rej_value)}]
+    for solver, (r, e, n, v) in zip(solvers, h_stats):
+        stats.append({f"{solver.name}_reward": host(r), f"{solver.name}_empty_bins": host(e),
+                      f"{solver.name}_num_rejected_items": host(n), f"{solver.name}_rejected_value": host(v)})
+    return stats, host(results).astype(np.int64)[0:3]
+
+
+def knapsack_log_testing_stats(global_stats, folder, file_name):
+    """knapsack_v2/misc/csv_writer.py:5-36: same header and columns; one row per instance of the batch."""
+    with open(f"{folder}/{file_name}.csv", "w") as fp:
+        header = "".join(f"{k};" for k in global_stats[0] if k != "instance")
+        for entry in global_stats[0]["instance"]:
+            header += "".join(f"{' '.join(k.split('_'))};" for k in list(entry.keys())[:4])
+        fp.write(f"{header}\n")
+        for st in global_stats:
+            batch = len(st["instance"][0]["net_reward"])
+            for b in range(batch):
+                data = (f"{st['test_instance'] * batch + b};{st['bin_sample_size']};{st['bin_min_value']};"
+                        f"{st['bin_max_value']};{st['item_sample_size']};")
+                for entry in st["instance"]:
+                    reward, empty, rejected, rej_value = list(entry.values())
+                    data += f"{reward[b]:.3f};{empty[b]};{rejected[b]};{rej_value[b]:.3f};"
+                fp.write(f"{data}\n")
+
+
 def knapsack_test(env, agent, opts: dict, log_dir: str):
-    """KnapsackV2: greedy rollouts over the test bed's (items, bins) cells; returns the per-instance collected value
-    (episode reward) and the number of items sent to the EOS bin. The reference's KnapsackV2 heuristics (OR-Tools,
-    waste reduction; environment/custom/knapsack_v2/heuristic/*) are a 'next' row."""
+    """knapsack_v2/tester.py:14-99 -> global_reward_results [won, draw, lost] of the net against the best heuristic
+    (waste-reduction combos and random; the reference's ORTools solver needs Google OR-Tools and is left out)."""
     tb = opts["testbed"]
     batch_size = opts.get("batch_size", 1)
-    bins_cfg, items_cfg = tb["bin_sample_configs"], tb["item_sample_configs"]
-    values, rejected = [], []
-    for item_size in range(items_cfg["min"], items_cfg["max"] + 1, items_cfg["step"]):
-        for bin_size in range(bins_cfg["min"], bins_cfg["max"] + 1, bins_cfg["step"]):
-            for _ in range(tb["num_tests"]):
-                env.set_testing_mode(batch_size, bin_size, item_size)
-                agent.set_testing_mode(batch_size, env.node_sample_size, env.profiles_sample_size)
-                bufs = env.device_buffers(store=False)
-                env.reset_into(bufs)
-                agent.rollout(env, bufs, greedy=True)
-                values.append(bufs.rewards.sum(dim=1).cpu().numpy())
-                rejected.append((bufs.actions == 0).sum(dim=0).cpu().numpy())
-    return np.concatenate(values), np.concatenate(rejected)
+    bins_cfg, cap_cfg, items_cfg = tb["bin_sample_configs"], tb["bin_available_capacities"], tb["item_sample_configs"]
+    gs = opts["export_stats"]["global_stats"]
+    filename = gs["filename"] if gs["filename"] is not None else generate_file_name(agent.agent_config)
+    global_stats = []
+    global_reward_results = np.zeros(3, dtype=np.int64)
+    for item_sample_size in range(items_cfg["min"], items_cfg["max"] + 1, items_cfg["step"]):
+        for bin_sample_size in range(bins_cfg["min"], bins_cfg["max"] + 1, bins_cfg["step"]):
+            for bin_min_value in range(cap_cfg["min"], cap_cfg["max"], cap_cfg["step"]):
+                for index in range(tb["num_tests"]):
+                    instance_stats, reward_result = knapsack_test_single_instance(
+                        index, env, agent, opts, batch_size, bin_sample_size, bin_min_value,
+                        bin_min_value + cap_cfg["step"], item_sample_size, log_dir)
+                    global_reward_results += reward_result
+                    global_stats.append({"test_instance": index, "bin_sample_size": bin_sample_size,
+                                         "bin_min_value": bin_min_value,
+                                         "bin_max_value": bin_min_value + cap_cfg["step"],
+                                         "item_sample_size": item_sample_size, "instance": instance_stats})
+    if gs["export_stats"] and log_dir is not None:
+        folder = os.path.join(log_dir, gs["folder"])
+        os.makedirs(folder, exist_ok=True)
+        knapsack_log_testing_stats(global_stats, folder, filename)
+    knapsack_test.global_stats = global_stats
+    return global_reward_results
