@@ -1,3 +1,6 @@
 cd tests/gpu_checks/micro
-./gemm_phase 1546240 128 1 0 512 | head -16
-./gemm_phase 1546240 512 1 1 128 | head -12
+for cfg in "1546240 128 1 0 512" "1546240 128 1 0 384"; do
+  echo "base:   $(./gemm_plain $cfg | head -1)"
+  echo "direct: $(./gemm_direct $cfg | head -1)"
+done
+./gemm_direct_prof 1546240 128 1 0 512 | head -16
