@@ -26,6 +26,12 @@ int main(int argc, char** argv) {
   if (ln) { e.aux = res; e.ldaux = 128; e.aux_mode = 1; }
   e.round_out = 0;
   if (!ln) e.relu = 1;
+  const int maskmode = argc > 6 ? atoi(argv[6]) : 0;   // 1: relu epilogue writes the bit image; 2: gate by the bit image; 3: gate by aux (in place)
+  uint32_t* mask = nullptr;
+  if (maskmode == 1 || maskmode == 2) { cudaMalloc(&mask, (size_t)M * (N / 32) * 4); cudaMemset(mask, 0xa5, (size_t)M * (N / 32) * 4); }
+  if (maskmode == 1) { e.mask_out = mask; e.mask_ld = N / 32; }
+  if (maskmode == 2) { e.relu = 0; e.bias = nullptr; e.mask_in = mask; e.mask_ld = N / 32; }
+  if (maskmode == 3) { e.relu = 0; e.bias = nullptr; e.aux = D; e.ldaux = N; e.aux_mode = 2; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0;
   for (int rep = 0; rep < 4; ++rep) {

@@ -1,6 +1,6 @@
 cd tests/gpu_checks/micro
-for cfg in "1546240 128 1 0 512" "1546240 128 1 0 384"; do
-  echo "base:   $(./gemm_plain $cfg | head -1)"
-  echo "direct: $(./gemm_direct $cfg | head -1)"
-done
-./gemm_direct_prof 1546240 128 1 0 512 | head -16
+echo "fwd FFN1 no mask : $(./gemm_plain 1546240 128 1 0 512 0 | head -1)"
+echo "fwd FFN1 mask out: $(./gemm_plain 1546240 128 1 0 512 1 | head -1)"
+echo "no gate          : $(./gemm_plain 1546240 128 0 0 512 0 | head -1)"
+echo "gate by aux h    : $(./gemm_plain 1546240 128 0 0 512 3 | head -1)"
+echo "gate by bit image: $(./gemm_plain 1546240 128 0 0 512 2 | head -1)"

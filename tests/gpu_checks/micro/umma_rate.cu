@@ -7,20 +7,33 @@ using namespace tpc;
 unsigned long long g_tpc_launches = 0;
 
 template <int MODE, int N>
-__global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
+__global__ void __launch_bounds__(320, 1) k(int iters, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint64_t bars[4];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < (6 * 16384 + 2 * 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  for (int i = threadIdx.x; i < (6 * 16384 + 2 * 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc<512>(&slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = slot;
+  if (MODE >= 6 && warp >= 1) {
+    // the other roles of the GEMM kernels: 9 warps spinning on an mbarrier that completes when the MMA stream ends
+    if (MODE == 6) mbar_wait(&bars[3], 0);
+    if (MODE == 7) {   // same wait with a suspend-time hint: the hardware parks the thread instead of re-probing
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "SPIN_LOOP:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+          "@p bra SPIN_DONE;\n\t"
+          "bra SPIN_LOOP;\n\t"
+          "SPIN_DONE:\n\t}" ::"r"(smem_u32(&bars[3])), "r"(0u), "r"(1000000u) : "memory");
+    }
+  }
   if (threadIdx.x == 0) {
     constexpr uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
     const long long t0 = clock64();
@@ -46,11 +59,12 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
         }
       }
       if (MODE >= 4) umma_commit(&bars[st]);          // per-k-block commit to a stage barrier (never waited on)
-      if (MODE >= 5) { mbar_try_wait(&bars[3], 1); tc_fence_after(); }   // the wait + fence of the next k-block
+      if (MODE == 5) { mbar_try_wait(&bars[3], 1); tc_fence_after(); }   // the wait + fence of the next k-block
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0);
     const long long t1 = clock64();
+    if (MODE >= 6) mbar_arrive(&bars[3]);
     if (blockIdx.x == 0) out[0] = t1 - t0;
   }
   tc_fence_before();
@@ -63,7 +77,7 @@ void run(const char* name, long long* d) {
   const int iters = 4000, smem = 6 * 16384 + 2 * 32768 + 2048;
   cudaFuncSetAttribute(k<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int grid : {1, 148}) {
-    k<MODE, N><<<grid, 128, smem>>>(iters, d);
+    k<MODE, N><<<grid, MODE >= 6 ? 320 : 128, smem>>>(iters, d);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
     const double n_mma = iters * 4.0 * (MODE >= 2 ? 3 : 1);
@@ -80,5 +94,7 @@ int main() {
   run<3, 128>("3xTF32 triple TS,TS,TS", d);
   run<4, 128>("  + commit per k-block", d);
   run<5, 128>("  + try_wait + fence", d);
+  run<6, 128>("  + 9 warps spinning (lean)", d);
+  run<7, 128>("  + 9 warps, suspend hint", d);
   return 0;
 }

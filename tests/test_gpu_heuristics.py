@@ -287,3 +287,28 @@ def test_knapsack_tester_sweep(tmp_path):
     (rw, _, rej, rv), values = knapsack_net_stats(bufs, init, env.node_sample_size)
     total = bufs.rewards.sum(dim=1)
     assert torch.allclose(rw, total, atol=1e-5) and torch.all((rej == 0) == (rv == 0))
+
+
+def test_reference_heuristic_unit_test_instances():
+    """The solver known-answer tests the reference holds: resource_v3/heuristic_test.py:196-236 (RandomHeuristic on
+    the un-normalised instance: whatever the draws, delta 1, one rejected rule, one empty node) and
+    knapsack_v2/heuristic_test.py:236-300, 303-410 (WasteReduction and Random on the 2-bin / 4-item instance)."""
+    from tpc_b200.heuristics import KnapsackRandomHeuristic, RandomHeuristic, WasteReductionHeuristic
+    for seed in range(8):
+        sol = RandomHeuristic(3, 100, {}, DEV, seed=seed)
+        sol.solve(G["kat_state"][None])
+        dom, rej, emp = (int(t.cpu().numpy()[0]) for t in sol.stats())
+        assert (dom, rej, emp) == (1, 1, 1)
+    kat = np.array([[-2.0, -2.0], [0.1, 0.0], [0.5, 0.0], [0.2, 0.1], [0.3, 0.5], [0.1, 0.4], [0.9, 0.4]], dtype=np.float32)
+    sol = WasteReductionHeuristic(3, {"item_sort_descending": True, "bin_sort_descending": False}, DEV)
+    sol.solve(kat[None])
+    rw, emp, rej, rv = (t.cpu().numpy()[0] for t in sol.stats())
+    a = sol.solution.assign.cpu().numpy()[0]
+    assert round(float(rw), 2) == 1.0 and (int(emp), int(rej)) == (0, 1) and rv == np.float32(0.4)
+    assert [int((a == n).sum()) for n in range(3)] == [1, 1, 2]
+    for seed in range(8):      # random: item 3 (weight 0.9) never fits, every other item fits some bin or is rejected
+        sol = KnapsackRandomHeuristic(3, {}, DEV, seed=seed)
+        sol.solve(kat[None])
+        a = sol.solution.assign.cpu().numpy()[0]
+        bins = sol.solution.bins.cpu().numpy()[0]
+        assert a[3] == 0 and np.all(bins[1:, 1] <= bins[1:, 0])

@@ -43,3 +43,15 @@ def test_random_replays_reference_draws(idx):
     a, order, bins, values = oh.knapsack_random(st, n_bins, randrange)
     _check(f"c{idx}_rnd", a, order, bins, values, st, n_bins)
     assert next(it, None) is None
+
+
+KN_KAT = np.array([[-2.0, -2.0], [0.1, 0.0], [0.5, 0.0], [0.2, 0.1], [0.3, 0.5], [0.1, 0.4], [0.9, 0.4]], dtype=np.float32)
+
+
+def test_reference_unit_test_instance():
+    """tests/unit/environment/knapsack_v2/heuristic_test.py:236-300 (WasteReduction, items descending / bins
+    ascending): reward 1.0, no empty bin, one rejected item worth 0.4, item counts per bin 1 / 1 / 2."""
+    a, order, bins, values = oh.knapsack_waste_reduction(KN_KAT, 3, True, False)
+    reward, empty, rejected, rej_value = oh.knapsack_solution_stats(a, values)
+    assert round(float(reward), 2) == 1.0 and (empty, rejected) == (0, 1) and rej_value == np.float32(0.4)
+    assert [int((a == n).sum()) for n in range(3)] == [1, 1, 2]

@@ -90,6 +90,9 @@ struct GemmArgs {
   int aux_mode, relu, ln, round_out, atomic;
   int split;   // 3xTF32: D = A.B + A_lo.B + A.B_lo with A_lo = A - trunc(A) built on chip, B_lo from the weight image
   float ln_eps;
+  uint32_t* mask_out;         // ReLU bit image (weight-resident kernel, MASK template variants)
+  const uint32_t* mask_in;
+  int mask_ld;
 };
 
 // byte offset of (row, col) inside the staging tile: 4 boxes [128 rows][32 cols], rows of 128 B, 16-byte chunks
@@ -395,8 +398,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (g.ln) {
         // whole row (N == 128) in registers: bias + residual, two-pass mean / variance, scale + shift
         float v[128];
+        {   // four loads in flight, one wait
+          uint32_t rv[4][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + c * 32, v + c * 32);
+          for (int c = 0; c < 4; ++c) tmem_ld_32x32_nowait(taddr + c * 32, rv[c]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 128; ++j) v[j] = __uint_as_float(rv[j >> 5][j & 31]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator drained: MMA may start the next-but-one tile
@@ -507,7 +516,10 @@ struct Bres {
   static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + 256 + 1024;
 };
 
-template <bool SPLIT>
+// MASK: 0 none | 1 the relu epilogue also writes the sign of its output as a bit image | 2 the output is gated by a
+// bit image (ReLU backward). Compile-time so that the plain epilogue -- a latency-critical per-chunk chain -- stays as
+// it is.
+template <bool SPLIT, int MASK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
@@ -708,9 +720,19 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // right away; boxes form a ring of NBUF, so the store of chunk c overlaps the TMEM load / math of chunk c+1.
       constexpr int NBUF = C::EPI_B / TILE_BYTES;       // 2 (3xTF32) or 4
       int cidx = 0;
+      // MASK == 2: the four gate words of (row, this column tile) are one 16-byte load, issued one tile ahead
+      auto load_gate = [&](int mt) {
+        const int r = mt * BM + et;
+        return (mt < m_tiles && r < g.M) ? __ldg(reinterpret_cast<const uint4*>(g.mask_in + (size_t)r * g.mask_ld + n_t * 4))
+                                         : make_uint4(0u, 0u, 0u, 0u);
+      };
+      uint4 gate_next = make_uint4(0u, 0u, 0u, 0u);
+      if (MASK == 2) gate_next = load_gate(m0);
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const uint4 gate_w = gate_next;
+        if (MASK == 2) gate_next = load_gate(m_t + groups);
         GP_T0();
         mbar_wait(&tfull[acc], acc_phase);
         if (leader) GP_ADD(9);
@@ -732,6 +754,8 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          const uint32_t gw = c == 0 ? gate_w.x : (c == 1 ? gate_w.y : (c == 2 ? gate_w.z : gate_w.w));
+          uint32_t bits = 0u;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
@@ -740,9 +764,18 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (MASK == 2) {
+              o.x = (gw & (1u << (j4 * 4 + 0))) ? o.x : 0.f; o.y = (gw & (1u << (j4 * 4 + 1))) ? o.y : 0.f;
+              o.z = (gw & (1u << (j4 * 4 + 2))) ? o.z : 0.f; o.w = (gw & (1u << (j4 * 4 + 3))) ? o.w : 0.f;
+            }
+            if (MASK == 1)
+              bits |= (o.x > 0.f ? 1u << (j4 * 4 + 0) : 0u) | (o.y > 0.f ? 1u << (j4 * 4 + 1) : 0u) |
+                      (o.z > 0.f ? 1u << (j4 * 4 + 2) : 0u) | (o.w > 0.f ? 1u << (j4 * 4 + 3) : 0u);
             if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
             *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
           }
+          if (MASK == 1 && m_t * BM + et < g.M)
+            g.mask_out[(size_t)(m_t * BM + et) * g.mask_ld + n_t * 4 + c] = bits;
           // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
           // older stores may still be in flight when the threads are released
           if (leader) GP_ADD(10);
@@ -1032,9 +1065,13 @@ int gemm_tc_init() {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_bres_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
+      e = cudaFuncSetAttribute(gemm_bres_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_bres_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_bres_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_bres_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
+      e = cudaFuncSetAttribute(gemm_bres_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) {
@@ -1081,6 +1118,12 @@ static int get_tmap(TmapCache* tc, const float* ptr, int rows, int cols, int ld,
   return TPC_OK;
 }
 
+bool gemm_weight_resident(int M, int N, int K, const GemmEpi& epi, bool split, int num_sms) {
+  const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
+  return (K == 128) && N % BN == 0 && !epi.ln && !epi.atomic && !(split && epi.aux_mode) && n_tiles <= num_sms &&
+         m_tiles * n_tiles >= 2 * num_sms;
+}
+
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
                 int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const float* Bt_lo) {
   TPC_TRY(gemm_tc_init());
@@ -1114,13 +1157,19 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     tAux = tD;
   }
   // weight-resident kernel: K == 128, no LayerNorm / split-K, (3xTF32: no aux), enough row tiles per CTA
-  const int m_tiles = ceil_div(M, BM);
-  const bool bres = (K == 128) && !epi.ln && !epi.atomic && !(g.split && epi.aux_mode) && g.n_tiles <= num_sms &&
-                    m_tiles * g.n_tiles >= 2 * num_sms;
+  const bool bres = gemm_weight_resident(M, N, K, epi, g.split != 0, num_sms);
+  g.mask_out = epi.mask_out; g.mask_in = epi.mask_in; g.mask_ld = epi.mask_ld;
+  if (epi.mask_out || epi.mask_in) {
+    // bit images: 16-byte aligned rows, mask_out from the 3xTF32 relu epilogue, mask_in into a single-pass GEMM
+    if (!bres || epi.aux_mode || epi.mask_ld < N / 32 || epi.mask_ld % 4 != 0 || (epi.mask_out && epi.mask_in)) return TPC_ERR_ARG;
+    if ((epi.mask_out && !(g.split && epi.relu)) || (epi.mask_in && g.split)) return TPC_ERR_ARG;
+  }
   if (bres) {
     int grid = (num_sms / g.n_tiles) * g.n_tiles;
-    if (g.split) gemm_bres_kernel<true><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
-    else gemm_bres_kernel<false><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    if (epi.mask_out) gemm_bres_kernel<true, 1><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else if (epi.mask_in) gemm_bres_kernel<false, 2><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else if (g.split) gemm_bres_kernel<true, 0><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else gemm_bres_kernel<false, 0><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
     TPC_CHECK_LAUNCH();
     return TPC_OK;
   }

@@ -46,7 +46,11 @@ struct Ctx {
 
 struct MaskRef { const float* mask; int mS; int m0; };  // mask[c * mS + m0 + j]
 
-struct EncLayerActs { float *qkv, *lse, *att, *out1, *rstd1, *h, *out2, *rstd2; };
+struct EncLayerActs {
+  float *qkv, *lse, *att, *out1, *rstd1, *h, *out2, *rstd2;
+  uint32_t* hmask;        // ReLU bit image of h: rows x dff / 32 words
+  bool has_mask = false;  // written by the forward pass (weight-resident FFN1 GEMM of a training context)
+};
 struct EncActs {
   float *emb_b = nullptr, *emb_r = nullptr, *cat = nullptr;
   std::vector<EncLayerActs> bins, res, joint;
@@ -109,6 +113,7 @@ void alloc_layer(Arena& ar, EncLayerActs& a, int rows, int dff) {
   a.out1 = ar.f((size_t)rows * 128);
   a.rstd1 = ar.f(rows);
   a.h = ar.f((size_t)rows * dff);
+  a.hmask = reinterpret_cast<uint32_t*>(ar.f((size_t)rows * (dff / 32)));
   a.out2 = ar.f((size_t)rows * 128);
   a.rstd2 = ar.f(rows);
 }
@@ -122,6 +127,9 @@ int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int L
                epi_ln(cx, cx.P + lp.mha.o.b, x, lp.ln1, a.rstd1)));
   GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
   e1.relu = 1;
+  // training context: the FFN1 epilogue also leaves the sign of h as a bit image for the ReLU backward
+  a.has_mask = cx.G != nullptr && dff % 128 == 0 && gemm_weight_resident(rows, dff, 128, e1, true, cx.sms());
+  if (a.has_mask) { e1.mask_out = a.hmask; e1.mask_ld = dff / 32; }
   TPC_TRY(gemm_fwd(cx, a.out1, 128, cx.W + lp.s.w1_t, 128, a.h, dff, rows, dff, 128, e1));
   TPC_TRY(gemm_fwd(cx, a.h, dff, cx.W + lp.s.w2_t, dff, a.out2, 128, rows, 128, dff,
                epi_ln(cx, cx.P + lp.f2.b, a.out1, lp.ln2, a.rstd2)));
@@ -138,9 +146,13 @@ int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int 
   RUN(ln_bwd(dout, dmap, a.out2, a.rstd2, cx.P + lp.ln2.g, cx.P + lp.ln2.b, rows, s.dA, cx.G + lp.ln2.g,
              cx.G + lp.ln2.b, cx.st));
   TPC_TRY(dense_grads(cx, a.h, dff, s.dA, 128, rows, lp.f2));
-  {  // dH = (dpre2 @ W2^T) * (h > 0), in place over h
+  {  // dH = (dpre2 @ W2^T) * (h > 0), written over h
     GemmEpi e;
-    e.aux = a.h; e.ldaux = dff; e.aux_mode = 2;
+    if (a.has_mask && gemm_weight_resident(rows, dff, 128, e, false, cx.sms())) {
+      e.mask_in = a.hmask; e.mask_ld = dff / 32;   // 16 B per row tile instead of re-reading 512 B of h
+    } else {
+      e.aux = a.h; e.ldaux = dff; e.aux_mode = 2;
+    }
     TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.w2_c, 128, a.h, dff, rows, dff, 128, e));
   }
   TPC_TRY(dense_grads(cx, a.out1, 128, a.h, dff, rows, lp.f1));
