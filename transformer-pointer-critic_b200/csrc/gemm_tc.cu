@@ -398,14 +398,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (g.ln) {
         // whole row (N == 128) in registers: bias + residual, two-pass mean / variance, scale + shift
         float v[128];
-        {   // four loads in flight, one wait
-          uint32_t rv[4][32];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_32x32_nowait(taddr + c * 32, rv[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 128; ++j) v[j] = __uint_as_float(rv[j >> 5][j & 31]);
-        }
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + c * 32, v + c * 32);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator drained: MMA may start the next-but-one tile
@@ -720,19 +714,19 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // right away; boxes form a ring of NBUF, so the store of chunk c overlaps the TMEM load / math of chunk c+1.
       constexpr int NBUF = C::EPI_B / TILE_BYTES;       // 2 (3xTF32) or 4
       int cidx = 0;
-      // MASK == 2: the four gate words of (row, this column tile) are one 16-byte load, issued one tile ahead
+      // MASK == 2: the four gate words of (row, this column tile) are one 16-byte load, issued two tiles ahead
       auto load_gate = [&](int mt) {
         const int r = mt * BM + et;
         return (mt < m_tiles && r < g.M) ? __ldg(reinterpret_cast<const uint4*>(g.mask_in + (size_t)r * g.mask_ld + n_t * 4))
                                          : make_uint4(0u, 0u, 0u, 0u);
       };
-      uint4 gate_next = make_uint4(0u, 0u, 0u, 0u);
-      if (MASK == 2) gate_next = load_gate(m0);
+      uint4 gate_next = make_uint4(0u, 0u, 0u, 0u), gate_next2 = make_uint4(0u, 0u, 0u, 0u);
+      if (MASK == 2) { gate_next = load_gate(m0); gate_next2 = load_gate(m0 + groups); }   // two tiles ahead: the words come from DRAM
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const uint4 gate_w = gate_next;
-        if (MASK == 2) gate_next = load_gate(m_t + groups);
+        if (MASK == 2) { gate_next = gate_next2; gate_next2 = load_gate(m_t + 2 * groups); }
         GP_T0();
         mbar_wait(&tfull[acc], acc_phase);
         if (leader) GP_ADD(9);
@@ -755,7 +749,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           const uint32_t gw = c == 0 ? gate_w.x : (c == 1 ? gate_w.y : (c == 2 ? gate_w.z : gate_w.w));
-          uint32_t bits = 0u;
+          uint32_t part[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
@@ -768,14 +762,15 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o.x = (gw & (1u << (j4 * 4 + 0))) ? o.x : 0.f; o.y = (gw & (1u << (j4 * 4 + 1))) ? o.y : 0.f;
               o.z = (gw & (1u << (j4 * 4 + 2))) ? o.z : 0.f; o.w = (gw & (1u << (j4 * 4 + 3))) ? o.w : 0.f;
             }
-            if (MASK == 1)
-              bits |= (o.x > 0.f ? 1u << (j4 * 4 + 0) : 0u) | (o.y > 0.f ? 1u << (j4 * 4 + 1) : 0u) |
-                      (o.z > 0.f ? 1u << (j4 * 4 + 2) : 0u) | (o.w > 0.f ? 1u << (j4 * 4 + 3) : 0u);
+            if (MASK == 1)   // eight independent 4-bit groups (one OR chain over 32 elements would serialise the chunk)
+              part[j4] = (o.x > 0.f ? 1u << (j4 * 4 + 0) : 0u) | (o.y > 0.f ? 1u << (j4 * 4 + 1) : 0u) |
+                         (o.z > 0.f ? 1u << (j4 * 4 + 2) : 0u) | (o.w > 0.f ? 1u << (j4 * 4 + 3) : 0u);
             if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
             *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
           }
           if (MASK == 1 && m_t * BM + et < g.M)
-            g.mask_out[(size_t)(m_t * BM + et) * g.mask_ld + n_t * 4 + c] = bits;
+            g.mask_out[(size_t)(m_t * BM + et) * g.mask_ld + n_t * 4 + c] =
+                ((part[0] | part[1]) | (part[2] | part[3])) | ((part[4] | part[5]) | (part[6] | part[7]));
           // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
           // older stores may still be in flight when the threads are released
           if (leader) GP_ADD(10);
