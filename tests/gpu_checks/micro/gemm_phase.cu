@@ -28,9 +28,10 @@ int main(int argc, char** argv) {
   if (!ln) e.relu = 1;
   const int maskmode = argc > 6 ? atoi(argv[6]) : 0;   // 1: relu epilogue writes the bit image; 2: gate by the bit image; 3: gate by aux (in place)
   uint32_t* mask = nullptr;
-  if (maskmode == 1 || maskmode == 2) { cudaMalloc(&mask, (size_t)M * (N / 32) * 4); cudaMemset(mask, 0xa5, (size_t)M * (N / 32) * 4); }
-  if (maskmode == 1) { e.mask_out = mask; e.mask_ld = N / 32; }
-  if (maskmode == 2) { e.relu = 0; e.bias = nullptr; e.mask_in = mask; e.mask_ld = N / 32; }
+  const int Mpad = (M + 127) / 128 * 128;
+  if (maskmode == 1 || maskmode == 2) { cudaMalloc(&mask, (size_t)Mpad * (N / 32) * 4); cudaMemset(mask, 0xa5, (size_t)Mpad * (N / 32) * 4); }
+  if (maskmode == 1) { e.mask_out = mask; e.mask_ld = Mpad; }
+  if (maskmode == 2) { e.relu = 0; e.bias = nullptr; e.mask_in = mask; e.mask_ld = Mpad; }
   if (maskmode == 3) { e.relu = 0; e.bias = nullptr; e.aux = D; e.ldaux = N; e.aux_mode = 2; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0;

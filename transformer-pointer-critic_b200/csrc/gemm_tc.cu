@@ -499,15 +499,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // different column tiles of the same rows run side by side, so the activation tile comes from HBM once.
 // Epilogue: bias / ReLU / aux add / aux ReLU-gate / TF32 rounding (no LayerNorm, no split-K: generic kernel).
 // ---------------------------------------------------------------------------------------------------------
-template <bool SPLIT>
+template <bool SPLIT, int MASK = 0>
 struct Bres {
   static constexpr int NKB = 4;                                  // K = 128 = 4 k-blocks of 32
   static constexpr int B_KB_BYTES = (SPLIT ? 2 : 1) * TILE_BYTES; // hi (+ lo) of one k-block
   static constexpr int B_BYTES = NKB * B_KB_BYTES;               // 64 KB / 128 KB
-  static constexpr int ASTAGES = SPLIT ? 4 : 6;                  // 16 KB activation k-blocks in flight
+  static constexpr int ASTAGES = SPLIT ? 4 : (MASK == 2 ? 5 : 6); // 16 KB activation k-blocks in flight
   static constexpr int EPI_COLS = SPLIT ? 64 : 128;              // staging tile: half / full width
   static constexpr int EPI_B = BM * EPI_COLS * 4;
-  static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + 256 + 1024;
+  static constexpr int GATE_BOX = BM * 16;                       // MASK == 2: 4 gate words per row of a tile
+  static constexpr int GATE_B = MASK == 2 ? 4 * GATE_BOX : 0;    // ring of 4 tiles
+  static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + GATE_B + 256 + 1024;
 };
 
 // MASK: 0 none | 1 the relu epilogue also writes the sign of its output as a bit image | 2 the output is gated by a
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
-  using C = Bres<SPLIT>;
+  using C = Bres<SPLIT, MASK>;
 #ifdef GEMM_PROFILE
   __shared__ volatile long long gp_issue_t[8];
   __shared__ volatile long long gp_commit_t[8];
@@ -528,7 +530,8 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* bsm = smem;
   uint8_t* ring = smem + C::B_BYTES;
   uint8_t* epi = ring + C::ASTAGES * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::EPI_B);
+  uint8_t* gbox = epi + C::EPI_B;               // MASK == 2: gate-word boxes (2 KB each, contiguous in global memory)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbox + C::GATE_B);
   uint64_t* full = bars;                        // [ASTAGES]
   uint64_t* empty = full + C::ASTAGES;          // [ASTAGES]
   uint64_t* lofull = empty + C::ASTAGES;        // [ASTAGES]
@@ -714,19 +717,28 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // right away; boxes form a ring of NBUF, so the store of chunk c overlaps the TMEM load / math of chunk c+1.
       constexpr int NBUF = C::EPI_B / TILE_BYTES;       // 2 (3xTF32) or 4
       int cidx = 0;
-      // MASK == 2: the four gate words of (row, this column tile) are one 16-byte load, issued two tiles ahead
-      auto load_gate = [&](int mt) {
-        const int r = mt * BM + et;
-        return (mt < m_tiles && r < g.M) ? __ldg(reinterpret_cast<const uint4*>(g.mask_in + (size_t)r * g.mask_ld + n_t * 4))
-                                         : make_uint4(0u, 0u, 0u, 0u);
+      // MASK == 2: the gate words of (this column tile, 128 rows) are 2 KB contiguous in global memory (image layout
+      // [column tile][row][4 words]); the leader brings them in three tiles ahead with a bulk copy into a ring of four
+      // boxes (per-thread loads of these words cost one exposed DRAM latency per tile, whatever the prefetch distance)
+      const int my_tiles_g = (m_tiles - m0 + groups - 1) / groups;
+      auto issue_gate = [&](int ti) {
+        const int mt = m0 + ti * groups;
+        mbar_expect_tx(&auxfull[ti & 3], C::GATE_BOX);
+        bulk_load(gbox + (ti & 3) * C::GATE_BOX, g.mask_in + ((size_t)n_t * g.mask_ld + (size_t)mt * BM) * 4, C::GATE_BOX,
+                  &auxfull[ti & 3]);
       };
-      uint4 gate_next = make_uint4(0u, 0u, 0u, 0u), gate_next2 = make_uint4(0u, 0u, 0u, 0u);
-      if (MASK == 2) { gate_next = load_gate(m0); gate_next2 = load_gate(m0 + groups); }   // two tiles ahead: the words come from DRAM
+      if (MASK == 2 && leader)
+        for (int ti = 0; ti < 3 && ti < my_tiles_g; ++ti) issue_gate(ti);
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const uint4 gate_w = gate_next;
-        if (MASK == 2) { gate_next = gate_next2; gate_next2 = load_gate(m_t + 2 * groups); }
+        uint4 gate_w = make_uint4(0u, 0u, 0u, 0u);
+        if (MASK == 2) {
+          // box (it + 3) & 3 was last read at the top of tile it - 1; every thread has passed a named barrier since
+          if (leader && it + 3 < my_tiles_g) issue_gate(it + 3);
+          mbar_wait(&auxfull[it & 3], (it >> 2) & 1);
+          gate_w = *reinterpret_cast<const uint4*>(gbox + (it & 3) * C::GATE_BOX + et * 16);
+        }
         GP_T0();
         mbar_wait(&tfull[acc], acc_phase);
         if (leader) GP_ADD(9);
@@ -769,7 +781,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
           }
           if (MASK == 1 && m_t * BM + et < g.M)
-            g.mask_out[(size_t)(m_t * BM + et) * g.mask_ld + n_t * 4 + c] =
+            g.mask_out[((size_t)n_t * g.mask_ld + m_t * BM + et) * 4 + c] =
                 ((part[0] | part[1]) | (part[2] | part[3])) | ((part[4] | part[5]) | (part[6] | part[7]));
           // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
           // older stores may still be in flight when the threads are released
@@ -1064,7 +1076,7 @@ int gemm_tc_init() {
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_bres_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_bres_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
+        e = cudaFuncSetAttribute(gemm_bres_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false, 2>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_bres_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<false>::SMEM);
     if (e == cudaSuccess)
@@ -1156,13 +1168,14 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   g.mask_out = epi.mask_out; g.mask_in = epi.mask_in; g.mask_ld = epi.mask_ld;
   if (epi.mask_out || epi.mask_in) {
     // bit images: 16-byte aligned rows, mask_out from the 3xTF32 relu epilogue, mask_in into a single-pass GEMM
-    if (!bres || epi.aux_mode || epi.mask_ld < N / 32 || epi.mask_ld % 4 != 0 || (epi.mask_out && epi.mask_in)) return TPC_ERR_ARG;
+    // image layout [N / 128][mask_ld rows][4 words], mask_ld = M rounded up to a multiple of 128
+    if (!bres || epi.aux_mode || epi.mask_ld < M || epi.mask_ld % BM != 0 || (epi.mask_out && epi.mask_in)) return TPC_ERR_ARG;
     if ((epi.mask_out && !(g.split && epi.relu)) || (epi.mask_in && g.split)) return TPC_ERR_ARG;
   }
   if (bres) {
     int grid = (num_sms / g.n_tiles) * g.n_tiles;
     if (epi.mask_out) gemm_bres_kernel<true, 1><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
-    else if (epi.mask_in) gemm_bres_kernel<false, 2><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else if (epi.mask_in) gemm_bres_kernel<false, 2><<<grid, GEMM_THREADS, Bres<false, 2>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
     else if (g.split) gemm_bres_kernel<true, 0><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
     else gemm_bres_kernel<false, 0><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
     TPC_CHECK_LAUNCH();

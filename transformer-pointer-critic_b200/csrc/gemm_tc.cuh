@@ -18,9 +18,10 @@ struct GemmEpi {
   int round_out = 1;              // store RN-rounded TF32 values (the output feeds a tensor-core operand)
   int atomic = 0;                 // split-K: atomically accumulate into D (D pre-initialised), no other epilogue op
   float ln_eps = 1e-6f;
-  // ReLU mask as a bit image, 4 words (128 columns) per (row, column tile), mask_ld words per row (weight-resident
-  // kernel only, see gemm_weight_resident()): mask_out is written by a 3xTF32 relu epilogue (bit j of word c of tile
-  // n_t = output column 128 n_t + 32 c + j is positive), mask_in gates the output of a single-pass GEMM
+  // ReLU mask as a bit image (weight-resident kernel only, see gemm_weight_resident()), laid out
+  // [N / 128 column tiles][mask_ld rows][4 words], mask_ld = M rounded up to a multiple of 128 (so the words one CTA
+  // needs for a row tile are 2 KB contiguous): bit j of word c = output column 128 n_t + 32 c + j. mask_out is written
+  // by a 3xTF32 relu epilogue (bit = output positive), mask_in gates the output of a single-pass GEMM
   // (v = bit ? v : 0): the ReLU backward then reads 16 bytes per row tile instead of 512 bytes of saved activation.
   uint32_t* mask_out = nullptr;
   const uint32_t* mask_in = nullptr;

@@ -113,7 +113,7 @@ void alloc_layer(Arena& ar, EncLayerActs& a, int rows, int dff) {
   a.out1 = ar.f((size_t)rows * 128);
   a.rstd1 = ar.f(rows);
   a.h = ar.f((size_t)rows * dff);
-  a.hmask = reinterpret_cast<uint32_t*>(ar.f((size_t)rows * (dff / 32)));
+  a.hmask = reinterpret_cast<uint32_t*>(ar.f((size_t)((rows + 127) / 128 * 128) * (dff / 32)));   // [dff / 128][rows padded][4]
   a.out2 = ar.f((size_t)rows * 128);
   a.rstd2 = ar.f(rows);
 }
@@ -129,7 +129,7 @@ int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int L
   e1.relu = 1;
   // training context: the FFN1 epilogue also leaves the sign of h as a bit image for the ReLU backward
   a.has_mask = cx.G != nullptr && dff % 128 == 0 && gemm_weight_resident(rows, dff, 128, e1, true, cx.sms());
-  if (a.has_mask) { e1.mask_out = a.hmask; e1.mask_ld = dff / 32; }
+  if (a.has_mask) { e1.mask_out = a.hmask; e1.mask_ld = (rows + 127) / 128 * 128; }
   TPC_TRY(gemm_fwd(cx, a.out1, 128, cx.W + lp.s.w1_t, 128, a.h, dff, rows, dff, 128, e1));
   TPC_TRY(gemm_fwd(cx, a.h, dff, cx.W + lp.s.w2_t, dff, a.out2, 128, rows, 128, dff,
                epi_ln(cx, cx.P + lp.f2.b, a.out1, lp.ln2, a.rstd2)));
@@ -149,7 +149,7 @@ int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int 
   {  // dH = (dpre2 @ W2^T) * (h > 0), written over h
     GemmEpi e;
     if (a.has_mask && gemm_weight_resident(rows, dff, 128, e, false, cx.sms())) {
-      e.mask_in = a.hmask; e.mask_ld = dff / 32;   // 16 B per row tile instead of re-reading 512 B of h
+      e.mask_in = a.hmask; e.mask_ld = (rows + 127) / 128 * 128;   // 16 B per row tile instead of re-reading 512 B of h
     } else {
       e.aux = a.h; e.ldaux = dff; e.aux_mode = 2;
     }
