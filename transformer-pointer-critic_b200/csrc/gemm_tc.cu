@@ -732,7 +732,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        uint4 gate_w = make_uint4(0u, 0u, 0u, 0u);
+        uint4 gate_w = make_uint4(0u, 0u, 0u, 0u), bits_out = make_uint4(0u, 0u, 0u, 0u);
         if (MASK == 2) {
           // box (it + 3) & 3 was last read at the top of tile it - 1; every thread has passed a named barrier since
           if (leader && it + 3 < my_tiles_g) issue_gate(it + 3);
@@ -780,9 +780,14 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
             *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
           }
-          if (MASK == 1 && m_t * BM + et < g.M)
-            g.mask_out[((size_t)n_t * g.mask_ld + m_t * BM + et) * 4 + c] =
-                ((part[0] | part[1]) | (part[2] | part[3])) | ((part[4] | part[5]) | (part[6] | part[7]));
+          if (MASK == 1) {   // one coalesced 16-byte store per row and tile (image rows are padded to the tile)
+            const uint32_t wbits = ((part[0] | part[1]) | (part[2] | part[3])) | ((part[4] | part[5]) | (part[6] | part[7]));
+            if (c == 0) bits_out.x = wbits; else if (c == 1) bits_out.y = wbits; else if (c == 2) bits_out.z = wbits;
+            else {
+              bits_out.w = wbits;
+              *reinterpret_cast<uint4*>(g.mask_out + ((size_t)n_t * g.mask_ld + m_t * BM + et) * 4) = bits_out;
+            }
+          }
           // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
           // older stores may still be in flight when the threads are released
           if (leader) GP_ADD(10);
