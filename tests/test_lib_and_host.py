@@ -89,3 +89,58 @@ def test_training_log_csv_matches_reference_layout(tmp_path):
     assert lines[0] == "Step;Avg Reward;Max Reward;Min Reward;Value Loss;Bin Entropy;Total Bin Loss;Bin Policy Loss"
     assert lines[1] == "0;1.000;3.000;0.000;10.123;1.600;0.750;0.500"
     assert lines[2] == "1;2.500;4.000;1.000;9.000;1.500;0.500;0.250"
+
+
+def test_tester_csv_writers_match_reference_layout(tmp_path):
+    """resource_v3/misc/csv_writer.py:3-35 and knapsack_v2/misc/csv_writer.py:5-36: header built from the stats keys
+    ('_' -> ' '), one ';'-terminated row per instance, dominant / reward / rejected value with three decimals."""
+    import numpy as np
+    from tpc_b200.tester import knapsack_log_testing_stats, log_testing_stats
+    inst = [{"net_dominant": np.float32([0.1, 0.25]), "net_rejected": np.int32([1, 0]),
+             "net_empty_nodes": np.int32([2, 3]), "net_optimal": 0},
+            {"random_dominant": np.float32([0.0, 0.5]), "random_rejected": np.int32([4, 5]),
+             "random_empty_nodes": np.int32([0, 1]), "random_optimal": 0}]
+    stats = [{"test_instance": 3, "node_sample_size": 5, "node_min_value": 0, "node_max_value": 100,
+              "resource_sample_size": 10, "instance": inst}]
+    log_testing_stats(stats, str(tmp_path), "t")
+    lines = open(tmp_path / "t.csv").read().splitlines()
+    assert lines[0] == ("test_instance;node_sample_size;node_min_value;node_max_value;resource_sample_size;"
+                        "net dominant;net rejected;net empty nodes;net optimal;"
+                        "random dominant;random rejected;random empty nodes;random optimal;")
+    assert lines[1] == "6;5;0;100;10;0.100;1;2;0;0.000;4;0;0;"
+    assert lines[2] == "7;5;0;100;10;0.250;0;3;0;0.500;5;1;0;"
+    kinst = [{"net_reward": np.float32([1.5]), "net_empty_bins": np.int32([0]), "net_num_rejected_items": np.int32([2]),
+              "net_rejected_value": np.float32([0.4])}]
+    kstats = [{"test_instance": 0, "bin_sample_size": 5, "bin_min_value": 0, "bin_max_value": 100,
+               "item_sample_size": 10, "instance": kinst}]
+    knapsack_log_testing_stats(kstats, str(tmp_path), "k")
+    klines = open(tmp_path / "k.csv").read().splitlines()
+    assert klines[0] == ("test_instance;bin_sample_size;bin_min_value;bin_max_value;item_sample_size;"
+                         "net reward;net empty bins;net num rejected items;net rejected value;")
+    assert klines[1] == "0;5;0;100;10;1.500;0;2;0.400;"
+
+
+def test_heuristic_factories_follow_reference_order_and_names():
+    """heuristic/factory.py:16-71 (ResourceV3) and knapsack_v2/heuristic/factory.py:5-50: construction needs no GPU."""
+    from tpc_b200.heuristics import heuristic_factory, knapsack_heuristic_factory
+    opts = {"dominant_resource": {"generate_params_combos": True, "resource_sort_descending": True,
+                                  "node_sort_descending": True}, "random": {},
+            "cplex_greedy_and_critical": {"use": False}, "cplex_node_reduction": {"use": False}}
+    names = [s.name for s in heuristic_factory(6, 100, opts, "cpu")]
+    assert names == ["dominant_resource_ASC_True_node_ASC_True", "dominant_resource_ASC_True_node_ASC_False",
+                     "dominant_resource_ASC_False_node_ASC_True", "dominant_resource_ASC_False_node_ASC_False", "random"]
+    opts["dominant_resource"]["generate_params_combos"] = False
+    assert [s.name for s in heuristic_factory(6, 100, opts, "cpu")] == ["dominant_resource_ASC_True_node_ASC_True", "random"]
+    kopts = {"waste_reduction": {"generate_params_combos": True, "item_sort_descending": True,
+                                 "bin_sort_descending": False}, "random": {}, "or_tools": {}}
+    assert [s.name for s in knapsack_heuristic_factory(4, kopts, "cpu")] == \
+        ["item_ASC_True_bin_ASC_True", "item_ASC_True_bin_ASC_False", "item_ASC_False_bin_ASC_True",
+         "item_ASC_False_bin_ASC_False", "random"]
+    # without a CUDA device the solvers refuse to run instead of falling back to the CPU
+    import numpy as np
+    import pytest
+    import torch
+    if not torch.cuda.is_available():
+        from tpc_b200.lib import TpcError
+        with pytest.raises((TpcError, RuntimeError, AssertionError)):
+            heuristic_factory(3, 100, opts, "cpu")[0].solve(np.zeros((1, 5, 3), dtype=np.float32))
