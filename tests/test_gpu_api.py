@@ -178,3 +178,29 @@ def test_runner_writes_the_reference_artefacts(tmp_path):
     assert len(logs) == 3 and logs[1].startswith("0;") and len(logs[1].split(";")) == 8
     assert os.path.exists(os.path.join(log_dir, "model", "actor.npz"))
     assert os.path.exists(os.path.join(log_dir, "tests", "test.csv")) and dom.sum() == rej.sum() == 3
+
+
+@pytest.mark.parametrize("reward", ["single_node_dominant", "global_dominant", "reduced_node_usage"])
+def test_training_with_every_reward_type(tmp_path, reward):
+    """BASELINE config #3 (fair = global_dominant, cost = reduced_node_usage with the 4-feature node embedding) at a
+    small shape: sampled rollouts + A2C updates run, losses stay finite, weights move, rewards follow reward.py's sign
+    conventions (penalties are negative, environment/custom/resource_v3/reward.py:46-166)."""
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import ResourceEnvironmentV3
+    from tpc_b200.trainer import trainer
+    agent_cfg, trainer_cfg, env_cfg, _, _, _ = get_configs("ResourceV3", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=32, node_sample_size=6, profiles_sample_size=12)
+    env_cfg["reward"]["type"] = reward
+    env = ResourceEnvironmentV3("ResourceV3", env_cfg, "cuda:0")
+    env.add_stats_to_agent_config(agent_cfg)
+    assert agent_cfg["encoder_embedding"]["common"] == (reward != "reduced_node_usage")
+    agent = Agent("transformer", agent_cfg, "cuda:0", num_features=3, seed=11)
+    before = agent.critic.get_flat().copy()
+    out = trainer(env, agent, dict(trainer_cfg, n_iterations=3, store_model_weights=dict(
+        trainer_cfg["store_model_weights"], export_weights=False)), False, str(tmp_path))
+    assert all(np.isfinite(v) for buf in out for v in buf)
+    assert not np.array_equal(before, agent.critic.get_flat())
+    avg, mn, mx = out[0], out[1], out[2]
+    assert all(a <= b + 1e-6 for a, b in zip(mn, avg)) and all(a <= b + 1e-6 for a, b in zip(avg, mx))
