@@ -29,11 +29,13 @@ WORKLOAD = {"nodes": 50, "rules": 100, "batch_per_gpu": 1024}
 FLOP_PER_DECISION = 1618.7e6     # rollout + A2C update at 50x100
 
 
-def load_cfg(batch, nodes, rules):
+def load_cfg(batch, nodes, rules, reward="greedy"):
+    import copy
     from tpc_b200.configs import get_configs
     agent_cfg, trainer_cfg, env_cfg, tester_cfg, tuner_cfg, _ = get_configs("ResourceV3", "tpc")
-    env_cfg = dict(env_cfg)
+    env_cfg = copy.deepcopy(env_cfg)
     env_cfg.update(batch_size=batch, node_sample_size=nodes, profiles_sample_size=rules)
+    env_cfg["reward"]["type"] = reward
     return agent_cfg, env_cfg
 
 
@@ -149,7 +151,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, nodes, rules = args.batch or WORKLOAD["batch_per_gpu"], args.nodes, args.rules
-    agent_cfg, env_cfg = load_cfg(B, nodes, rules)
+    agent_cfg, env_cfg = load_cfg(B, nodes, rules, args.reward)
     env = ResourceEnvironmentV3("ResourceV3", env_cfg, dev)
     env.add_stats_to_agent_config(agent_cfg)
     agent = Agent("transformer", agent_cfg, dev, num_features=3, seed=0)
@@ -260,7 +262,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 forward, TF32 backward)",
         "data": "synthetic",
-        "config": {"workload": f"ResourceV3 {nodes} nodes x {rules} rules, batch {B}/GPU, greedy reward, rollout + A2C "
+        "config": {"workload": f"ResourceV3 {nodes} nodes x {rules} rules, batch {B}/GPU, {args.reward} reward, rollout + A2C "
                                f"update (actor 1 layer, critic 3 layers)",
                    "decisions_per_step": world * B * T, "chunk_states": chunk,
                    "l2": "working set per step (>4 GB of activations) far exceeds the 126 MB L2; no flush needed",
@@ -289,6 +291,8 @@ def main():
     ap.add_argument("--rules", type=int, default=WORKLOAD["rules"])
     ap.add_argument("--chunk", type=int, default=0, help="states per update chunk (default: ~10240, equal chunks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--reward", default="greedy", help="ResourceV3 reward type (BASELINE config #3: global_dominant = "
+                    "fair, reduced_node_usage = cost); the headline metric is quoted on greedy")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: native libraries (the NCCL version banner, for instance) write to file
     # descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and Python's sys.stdout keeps the real one.
