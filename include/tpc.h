@@ -259,6 +259,26 @@ int tpc_knapsack_stats(tpc_handle* h, const int32_t* assign, int64_t stride_inst
                        const float* values, int B, int num_bins, int num_items, float* reward, int32_t* empty_bins,
                        int32_t* rejected, float* rejected_value, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * step-wise loss arithmetic (the API-exact mode of Agent; tpc_a2c_grads does the same inside the fused update)
+ * ---------------------------------------------------------------------------------------------------- */
+/* replaces Agent.compute_discounted_rewards (agents/agent.py:110-124): rewards, returns (B,T); bootstrap (B) = value
+ * after the last step, NULL = 0 (agents/trainer.py:103-105). */
+int tpc_discounted_returns(tpc_handle* h, const float* rewards, const float* bootstrap, int B, int T, float gamma,
+                           float* returns, void* stream);
+/* replaces the arithmetic of Agent.compute_value_loss (agents/agent.py:155-164): returns_v, values, advantages (n)
+ * step-major; loss[0] = c_v * mean((R - V)^2). */
+int tpc_value_loss(tpc_handle* h, const float* returns_v, const float* values, int n, float c_v, float* advantages,
+                   float* loss, void* stream);
+/* replaces the arithmetic of Agent.compute_actor_loss (agents/agent.py:189-240): policy_loss (n) = sparse softmax
+ * cross-entropy of the taken action, entropy (n) (both optional); sums[3] = mean policy loss,
+ * mean(policy_loss * advantage - c_e * entropy), mean entropy. */
+int tpc_actor_loss(tpc_handle* h, const float* logits, const int32_t* actions, const float* advantages, int n, int S,
+                   float c_e, float* policy_loss, float* entropy, float* sums, void* stream);
+/* replaces the batch statistics of the training loop (agents/trainer.py:89-100): out[3] = min, max, mean over the
+ * batch of the per-episode returns (sum of the T step rewards of rewards (B,T)). */
+int tpc_episode_reward_stats(tpc_handle* h, const float* rewards, int B, int T, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

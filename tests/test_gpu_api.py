@@ -57,6 +57,31 @@ def test_stepwise_api_matches_oracle_and_fused_update():
     total, _, entropy, ploss, probs = agent.compute_actor_loss(agent.bin_actor, agent.bin_masks, agent.bins,
                                                                agent.actor_decoder_input, adv)
     np.testing.assert_almost_equal(np.concatenate(act_probs), np.asarray(probs), decimal=5)
+    # independent host recomputation (float64) of what the device loss kernels return (agents/agent.py:110-242)
+    rw = agent.rewards.astype(np.float64)
+    Rref = np.zeros_like(rw)
+    boot = np.zeros(rw.shape[0])
+    for step in reversed(range(rw.shape[1])):
+        boot = rw[:, step] + agent.gamma * boot
+        Rref[:, step] = boot
+    np.testing.assert_allclose(R, Rref, rtol=1e-6, atol=1e-6)
+    n = values.shape[0]
+    Rv = np.concatenate([Rref[:, t_] for t_ in range(rw.shape[1])])             # reshape_into_vertical_format
+    v64 = np.asarray(values, dtype=np.float64).reshape(-1)
+    np.testing.assert_allclose(np.asarray(adv).reshape(-1), Rv - v64, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(vloss, agent.values_loss_coefficient * np.mean((Rv - v64) ** 2), rtol=1e-5)
+    lg = np.asarray(agent.bin_actor(np.concatenate(agent.states), np.concatenate(agent.actor_decoder_input),
+                                    np.concatenate(agent.bin_masks), True, agent.num_bins,
+                                    enc_padding_mask=np.concatenate(agent.mha_masks),
+                                    dec_padding_mask=np.concatenate(agent.mha_masks))[0], dtype=np.float64)
+    mx = lg.max(axis=-1, keepdims=True)
+    logp = lg - (mx + np.log(np.exp(lg - mx).sum(axis=-1, keepdims=True)))
+    acts = np.concatenate([np.asarray(a) for a in agent.bins]).astype(np.int64).reshape(-1)
+    pl_ref = -logp[np.arange(n), acts]
+    ent_ref = -(np.exp(logp) * logp).sum(axis=-1)
+    np.testing.assert_allclose(np.asarray(ploss), pl_ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(np.asarray(entropy), ent_ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(total, np.mean(pl_ref * (Rv - v64) - agent.entropy_coefficient * ent_ref), rtol=1e-4, atol=1e-5)
     bufs = agent.memory_to_device()
     losses = agent.update(bufs).cpu().numpy()
     ref = np.array([vloss, np.mean(ploss), total, np.mean(entropy)], dtype=np.float64)
@@ -204,3 +229,23 @@ def test_training_with_every_reward_type(tmp_path, reward):
     assert not np.array_equal(before, agent.critic.get_flat())
     avg, mn, mx = out[0], out[1], out[2]
     assert all(a <= b + 1e-6 for a, b in zip(mn, avg)) and all(a <= b + 1e-6 for a, b in zip(avg, mx))
+
+
+def test_episode_reward_stats_kernel():
+    """trainer.py:89-100: min / max / mean over the batch of the per-episode returns."""
+    import ctypes as C
+    import torch
+    from tpc_b200 import lib as L
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.tpc_create(C.byref(h)) == 0
+    rng = np.random.default_rng(3)
+    for (B, T) in [(1, 1), (7, 5), (1024, 100), (4096, 20)]:
+        rw = rng.normal(size=(B, T)).astype(np.float32)
+        d = torch.as_tensor(rw).cuda()
+        out = torch.empty(3, device="cuda")
+        assert lib.tpc_episode_reward_stats(h, L.ptr(d), B, T, L.ptr(out),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        ret = rw.astype(np.float64).sum(axis=1)
+        np.testing.assert_allclose(out.cpu().numpy(), [ret.min(), ret.max(), ret.mean()], rtol=1e-5, atol=1e-5)
+    lib.tpc_destroy(h)

@@ -210,43 +210,57 @@ class Agent:
         return bin_ids, bins_mask, bins_probs
 
     def compute_discounted_rewards(self, bootstrap_state_value):
-        """agents/agent.py:110-124 (host arithmetic on the (B,T) reward table, as in the reference)."""
-        boot = np.asarray(bootstrap_state_value, dtype=np.float32).reshape(-1)
-        out = np.zeros_like(self.rewards)
-        for step in reversed(range(self.rewards.shape[1])):
-            est = self.rewards[:, step] + np.float32(self.gamma) * boot
-            out[:, step] = est
-            boot = est
-        return out
+        """agents/agent.py:110-124 -> (B,T) returns (device kernel tpc_discounted_returns)."""
+        eng = self.engine
+        B, T = self.rewards.shape
+        rw = _dev(self.rewards, eng.device)
+        boot = _dev(np.asarray(bootstrap_state_value, dtype=np.float32).reshape(-1), eng.device)
+        if boot.numel() != B:
+            raise ValueError(f"bootstrap_state_value must hold one value per episode ({B}), got {boot.numel()}")
+        out = torch.empty(B, T, dtype=torch.float32, device=eng.device)
+        L.check(eng.lib.tpc_discounted_returns(eng.h, L.ptr(rw), L.ptr(boot), B, T, float(self.gamma), L.ptr(out),
+                                               eng.stream), "tpc_discounted_returns")
+        return out.cpu().numpy()
 
     def compute_value_loss(self, discounted_rewards):
-        """agents/agent.py:126-166 -> (value_loss, state_values, advantages)."""
+        """agents/agent.py:126-166 -> (value_loss, state_values, advantages); arithmetic in tpc_value_loss."""
+        eng = self.engine
         states = np.concatenate(self.states, axis=0)
         n = states.shape[0]
         mha = np.concatenate(self.mha_masks, axis=0)
         values = np.asarray(self.critic(states, self.training, self.num_bins, enc_padding_mask=mha))
         R = reshape_into_vertical_format(discounted_rewards, n).astype(np.float32)
-        adv = R - values
-        loss = np.float32(self.values_loss_coefficient) * np.mean((R - values) ** 2, axis=-1)
-        return np.mean(loss, axis=-1), values.view(HostTensor), adv.view(HostTensor)
+        Rd, Vd = _dev(R.reshape(-1), eng.device), _dev(values.reshape(-1), eng.device)
+        adv = torch.empty(n, dtype=torch.float32, device=eng.device)
+        loss = torch.empty(1, dtype=torch.float32, device=eng.device)
+        L.check(eng.lib.tpc_value_loss(eng.h, L.ptr(Rd), L.ptr(Vd), n, float(self.values_loss_coefficient), L.ptr(adv),
+                                       L.ptr(loss), eng.stream), "tpc_value_loss")
+        return (np.float32(loss.cpu().numpy()[0]), values.view(HostTensor),
+                adv.cpu().numpy().reshape(n, 1).view(HostTensor))
 
     def compute_actor_loss(self, model, masks, actions, decoder_inputs, advantages):
-        """agents/agent.py:168-242 -> (total_loss, dec_output, entropy, policy_loss, probs)."""
+        """agents/agent.py:168-242 -> (total_loss, dec_output, entropy, policy_loss, probs); arithmetic in tpc_actor_loss."""
+        eng = self.engine
         states = np.concatenate(self.states, axis=0)
         attention_mask = np.concatenate(masks, axis=0)
         mha = np.concatenate(self.mha_masks, axis=0)
         dec_input = np.concatenate(decoder_inputs, axis=0)
         logits, probs, _idx, dec_out = model(states, dec_input, attention_mask, self.training, self.num_bins,
                                              enc_padding_mask=mha, dec_padding_mask=mha)
-        logits = np.asarray(logits, dtype=np.float32)
+        logits = np.ascontiguousarray(np.asarray(logits, dtype=np.float32))
         probs = np.asarray(probs, dtype=np.float32)
-        acts = np.concatenate([np.asarray(a) for a in actions], axis=0).astype(np.int64)
-        mx = logits.max(axis=-1, keepdims=True)
-        logp = logits - (mx + np.log(np.exp(logits - mx).sum(axis=-1, keepdims=True)))
-        policy_loss = -logp[np.arange(len(acts)), acts]
-        entropy = -(probs * logp).sum(axis=-1)
-        total = np.mean(policy_loss * np.asarray(advantages).reshape(-1) - self.entropy_coefficient * entropy, axis=-1)
-        return total, dec_out, entropy.view(HostTensor), policy_loss.view(HostTensor), probs.view(HostTensor)
+        n, S = logits.shape
+        acts = _dev(np.concatenate([np.asarray(a) for a in actions], axis=0).reshape(-1), eng.device, torch.int32)
+        adv = _dev(np.asarray(advantages, dtype=np.float32).reshape(-1), eng.device)
+        lg = _dev(logits, eng.device)
+        policy_loss = torch.empty(n, dtype=torch.float32, device=eng.device)
+        entropy = torch.empty(n, dtype=torch.float32, device=eng.device)
+        sums = torch.empty(3, dtype=torch.float32, device=eng.device)
+        L.check(eng.lib.tpc_actor_loss(eng.h, L.ptr(lg), L.ptr(acts), L.ptr(adv), n, S, float(self.entropy_coefficient),
+                                       L.ptr(policy_loss), L.ptr(entropy), L.ptr(sums), eng.stream), "tpc_actor_loss")
+        total = np.float32(sums.cpu().numpy()[1])
+        return (total, dec_out, entropy.cpu().numpy().view(HostTensor), policy_loss.cpu().numpy().view(HostTensor),
+                probs.view(HostTensor))
 
     # ------------------------------------------------------------------ fused device path
     def memory_to_device(self) -> RolloutTensors:

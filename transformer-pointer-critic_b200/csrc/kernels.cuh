@@ -66,13 +66,18 @@ int value_head_bwd(const float* dv, const float* h1, const float* Wv, int C, flo
 int fill_rows_bias(float* out, const float* bias, int rows, cudaStream_t st);
 int round_tf32_inplace(float* x, size_t n, cudaStream_t st);
 
-// Returns (agents/agent.py:110-124): rewards[B][T] -> R[t*B + b], bootstrap 0 (agents/trainer.py:103-105)
-int discounted_returns(const float* rewards, int B, int T, float gamma, float* R, cudaStream_t st);
-// critic loss pieces (agents/agent.py:155-164): adv = R - V, dv = -2 c_v (R - V) * inv_total, losses[0] += c_v (R-V)^2
+// Returns (agents/agent.py:110-124): rewards[B][T] -> R[t*B + b] (horizontal: R[b*T + t]); bootstrap[B] = value after
+// the last step (NULL = 0, agents/trainer.py:103-105)
+int discounted_returns(const float* rewards, int B, int T, float gamma, float* R, cudaStream_t st,
+                       const float* bootstrap = nullptr, int horizontal = 0);
+// critic loss pieces (agents/agent.py:155-164): adv = R - V, dv = -2 c_v (R - V) * inv_total (optional),
+// losses[0] += out_scale * sum c_v (R-V)^2
 int critic_loss_bwd(const float* R, const float* V, int n, float c_v, float inv_total, float* adv, float* dv,
-                    float* losses, cudaStream_t st);
-// actor loss pieces (agents/agent.py:189-240): dlogits = adv (softmax - onehot) * inv_total; losses[1..3]
+                    float* losses, cudaStream_t st, float out_scale = 1.f);
+// actor loss pieces (agents/agent.py:189-240): dlogits = adv (softmax - onehot) * inv_total (optional); per-state
+// sparse cross-entropy / entropy (optional); losses[1..3] += out_scale * sums of {policy loss, total, entropy}
 int actor_loss_bwd(const float* logits, const int32_t* actions, const float* adv, int n, int S, float c_e,
-                   float inv_total, float* dlogits, float* losses, cudaStream_t st);
+                   float inv_total, float* dlogits, float* losses, cudaStream_t st, float out_scale = 1.f,
+                   float* policy_out = nullptr, float* entropy_out = nullptr);
 
 }  // namespace tpc

@@ -343,36 +343,42 @@ __global__ void round_tf32_kernel(float* __restrict__ x, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-__global__ void returns_kernel(const float* __restrict__ rewards, int B, int T, float gamma, float* __restrict__ R) {
+// bootstrap: value after the last step per episode (NULL = 0, agents/trainer.py:103-105); horizontal: R laid out (B,T)
+// like the reference's return value instead of the step-major vector the critic consumes
+__global__ void returns_kernel(const float* __restrict__ rewards, const float* __restrict__ bootstrap, int B, int T,
+                               float gamma, int horizontal, float* __restrict__ R) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float boot = 0.f;
+  float boot = bootstrap ? bootstrap[b] : 0.f;
   for (int t = T - 1; t >= 0; --t) {
     // estimate = r + gamma * bootstrap (agents/agent.py:117-118), fp32, no fma contraction
     const float est = __fadd_rn(rewards[(size_t)b * T + t], __fmul_rn(gamma, boot));
-    R[(size_t)t * B + b] = est;
+    R[horizontal ? (size_t)b * T + t : (size_t)t * B + b] = est;
     boot = est;
   }
 }
 
 __global__ void critic_loss_bwd_kernel(const float* __restrict__ R, const float* __restrict__ V, int n, float c_v,
-                                       float inv_total, float* __restrict__ adv, float* __restrict__ dv,
+                                       float inv_total, float out_scale, float* __restrict__ adv, float* __restrict__ dv,
                                        float* __restrict__ losses) {
   float acc = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float a = R[i] - V[i];
     adv[i] = a;
-    dv[i] = -2.f * c_v * a * inv_total;
+    if (dv) dv[i] = -2.f * c_v * a * inv_total;
     acc = fmaf(c_v * a, a, acc);
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(losses + 0, acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(losses + 0, acc * out_scale);
 }
 
 // warp per state
+// dlogits / policy_out / entropy_out are optional; the three sums are scaled by out_scale (1 in the fused update, which
+// divides by the job-wide state count afterwards; 1 / n for the step-wise API's means)
 __global__ void actor_loss_bwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ actions,
                                       const float* __restrict__ adv, int n, int S, float c_e, float inv_total,
-                                      float* __restrict__ dlogits, float* __restrict__ losses) {
+                                      float out_scale, float* __restrict__ dlogits, float* __restrict__ policy_out,
+                                      float* __restrict__ entropy_out, float* __restrict__ losses) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
@@ -391,14 +397,16 @@ __global__ void actor_loss_bwd_kernel(const float* __restrict__ logits, const in
     const float logp = l[j] - lse;
     const float p = expf(logp);
     ent -= p * logp;  // masked entries: p == 0 exactly (logp ~ -1e9), contributes 0
-    dlogits[(size_t)i * S + j] = ad * (p - (j == a ? 1.f : 0.f)) * inv_total;
+    if (dlogits) dlogits[(size_t)i * S + j] = ad * (p - (j == a ? 1.f : 0.f)) * inv_total;
   }
   ent = warp_sum(ent);
   if (lane == 0) {
     const float pl = -(l[a] - lse);
-    atomicAdd(losses + 1, pl);
-    atomicAdd(losses + 2, pl * ad - c_e * ent);
-    atomicAdd(losses + 3, ent);
+    if (policy_out) policy_out[i] = pl;
+    if (entropy_out) entropy_out[i] = ent;
+    atomicAdd(losses + 1, pl * out_scale);
+    atomicAdd(losses + 2, (pl * ad - c_e * ent) * out_scale);
+    atomicAdd(losses + 3, ent * out_scale);
   }
 }
 
@@ -521,25 +529,31 @@ int round_tf32_inplace(float* x, size_t n, cudaStream_t st) {
   return TPC_OK;
 }
 
-int discounted_returns(const float* rewards, int B, int T, float gamma, float* R, cudaStream_t st) {
-  returns_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rewards, B, T, gamma, R);
+int discounted_returns(const float* rewards, int B, int T, float gamma, float* R, cudaStream_t st,
+                       const float* bootstrap, int horizontal) {
+  if (B <= 0 || T <= 0) return TPC_OK;
+  returns_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rewards, bootstrap, B, T, gamma, horizontal, R);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
 
 int critic_loss_bwd(const float* R, const float* V, int n, float c_v, float inv_total, float* adv, float* dv,
-                    float* losses, cudaStream_t st) {
+                    float* losses, cudaStream_t st, float out_scale) {
+  if (n <= 0) return TPC_OK;
   int blocks = ceil_div(n, 256);
   if (blocks > 296) blocks = 296;
-  critic_loss_bwd_kernel<<<blocks, 256, 0, st>>>(R, V, n, c_v, inv_total, adv, dv, losses);
+  critic_loss_bwd_kernel<<<blocks, 256, 0, st>>>(R, V, n, c_v, inv_total, out_scale, adv, dv, losses);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
 
 int actor_loss_bwd(const float* logits, const int32_t* actions, const float* adv, int n, int S, float c_e,
-                   float inv_total, float* dlogits, float* losses, cudaStream_t st) {
+                   float inv_total, float* dlogits, float* losses, cudaStream_t st, float out_scale, float* policy_out,
+                   float* entropy_out) {
+  if (n <= 0) return TPC_OK;
   actor_loss_bwd_kernel<<<blocks_for((long long)n * 32, 256), 256, 0, st>>>(logits, actions, adv, n, S, c_e, inv_total,
-                                                                             dlogits, losses);
+                                                                             out_scale, dlogits, policy_out, entropy_out,
+                                                                             losses);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

@@ -7,6 +7,37 @@ using namespace tpc;
 
 unsigned long long g_tpc_launches = 0;
 
+namespace {
+// per-episode return = sum over the T step rewards; out = {min, max, mean} over the batch (agents/trainer.py:89-100).
+// One CTA: the batch is a few thousand episodes at most.
+__global__ void __launch_bounds__(256) reward_stats_kernel(const float* __restrict__ rewards, int B, int T,
+                                                           float* __restrict__ out) {
+  __shared__ float smn[8], smx[8], ssum[8];
+  float mn = INFINITY, mx = -INFINITY, sum = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    float r = 0.f;
+    for (int t = 0; t < T; ++t) r += rewards[(size_t)b * T + t];
+    mn = fminf(mn, r);
+    mx = fmaxf(mx, r);
+    sum += r;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if ((threadIdx.x & 31) == 0) smn[threadIdx.x >> 5] = mn, smx[threadIdx.x >> 5] = mx, ssum[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mn = fminf(mn, smn[w]), mx = fmaxf(mx, smx[w]), sum += ssum[w];
+    out[0] = mn;
+    out[1] = mx;
+    out[2] = sum / (float)B;
+  }
+}
+}  // namespace
+
 extern "C" {
 
 unsigned long long tpc_launch_count(void) { return g_tpc_launches; }
@@ -92,4 +123,43 @@ int tpc_attention_bwd(tpc_handle* h, const float* qkv, const float* att, const f
   return attention_bwd(qkv, att, lse, datt, mask, mS, m0, C, L, dqkv, (cudaStream_t)stream);
 }
 
+
+// ---- step-wise loss arithmetic (the fused update does the same inside tpc_a2c_grads) --------------------------------
+// replaces Agent.compute_discounted_rewards (agents/agent.py:110-124): returns (B,T), bootstrap (B) may be NULL (= 0)
+int tpc_discounted_returns(tpc_handle* h, const float* rewards, const float* bootstrap, int B, int T, float gamma,
+                           float* returns, void* stream) {
+  if (!h || !rewards || !returns) return TPC_ERR_ARG;
+  if (B < 0 || T < 0) return TPC_ERR_SHAPE;
+  return discounted_returns(rewards, B, T, gamma, returns, (cudaStream_t)stream, bootstrap, 1);
+}
+// replaces the arithmetic of Agent.compute_value_loss (agents/agent.py:155-164): advantages = R - V,
+// loss[0] = c_v * mean((R - V)^2)
+int tpc_value_loss(tpc_handle* h, const float* returns_v, const float* values, int n, float c_v, float* advantages,
+                   float* loss, void* stream) {
+  if (!h || !returns_v || !values || !advantages || !loss) return TPC_ERR_ARG;
+  if (n < 0) return TPC_ERR_SHAPE;
+  TPC_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  return critic_loss_bwd(returns_v, values, n, c_v, 0.f, advantages, nullptr, loss, (cudaStream_t)stream,
+                         n > 0 ? 1.f / (float)n : 0.f);
+}
+// replaces the arithmetic of Agent.compute_actor_loss (agents/agent.py:189-240): per-state sparse cross-entropy and
+// entropy, sums[0..2] = mean policy loss, mean(policy_loss * advantage - c_e * entropy), mean entropy
+int tpc_actor_loss(tpc_handle* h, const float* logits, const int32_t* actions, const float* advantages, int n, int S,
+                   float c_e, float* policy_loss, float* entropy, float* sums, void* stream) {
+  if (!h || !logits || !actions || !advantages || !sums) return TPC_ERR_ARG;
+  if (n < 0 || S < 1) return TPC_ERR_SHAPE;
+  TPC_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), (cudaStream_t)stream));
+  return actor_loss_bwd(logits, actions, advantages, n, S, c_e, 0.f, nullptr, sums - 1, (cudaStream_t)stream,
+                        n > 0 ? 1.f / (float)n : 0.f, policy_loss, entropy);
+}
+
+// replaces the batch statistics of the training loop (agents/trainer.py:89-100): out[3] = min, max, mean over the
+// batch of the per-episode returns (sum of the T step rewards)
+int tpc_episode_reward_stats(tpc_handle* h, const float* rewards, int B, int T, float* out, void* stream) {
+  if (!h || !rewards || !out) return TPC_ERR_ARG;
+  if (B < 1 || T < 1) return TPC_ERR_SHAPE;
+  reward_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rewards, B, T, out);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
 }  // extern "C"

@@ -14,6 +14,7 @@ import time
 import numpy as np
 import torch
 
+from . import lib as L
 from .agent import Agent
 
 
@@ -53,8 +54,10 @@ def trainer(env, agent: Agent, opts: dict, show_progress: bool, log_dir: str):
         bufs, losses = train_iteration(env, agent, bufs)
         episode_count += 1
         # statistics (trainer.py:89-100,159-162): one small device->host read per iteration
-        per_problem = bufs.rewards.sum(dim=1)
-        stats = torch.stack([per_problem.min(), per_problem.max(), per_problem.mean()])
+        stats = torch.empty(3, dtype=torch.float32, device=bufs.rewards.device)
+        eng = agent.engine
+        L.check(eng.lib.tpc_episode_reward_stats(eng.h, L.ptr(bufs.rewards), bufs.B, bufs.R, L.ptr(stats), eng.stream),
+                "tpc_episode_reward_stats")
         if world > 1:
             mn, mx, av = stats[0:1].clone(), stats[1:2].clone(), stats[2:3].clone()
             dist.all_reduce(mn, op=dist.ReduceOp.MIN)
