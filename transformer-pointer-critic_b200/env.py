@@ -93,7 +93,9 @@ class _DeviceEnvBase:
                                        L.ptr(self.profiles), self.batch_size, self.node_sample_size,
                                        self.profiles_sample_size, L.ptr(self.batch_d), L.ptr(self.bin_net_mask_d),
                                        L.ptr(self.mha_mask_d), L.ptr(self.is_empty_d), self.stream), "tpc_env_reset")
-        self.resource_net_mask_d.copy_(1.0 - self.bin_net_mask_d)
+        # initial resource mask = complement of the initial bin mask (env.py:265-288): node positions 1, rule positions 0
+        self.resource_net_mask_d[:, :self.node_sample_size].fill_(1.0)
+        self.resource_net_mask_d[:, self.node_sample_size:].fill_(0.0)
         self.epoch += 1
         if self.gather_stats:
             self.history = None  # per-instance Python history objects are replaced by device statistics (tester.py)
