@@ -136,6 +136,30 @@ def init_params(spec, seed: int, use_default_initializer=True, dims=128) -> np.n
     return flat
 
 
+def golden_params(spec, seed: int) -> np.ndarray:
+    """Deterministic NON-trivial parameters for the golden model vectors (tests/golden/make_model_golden.py writes
+    these into the reference's variables in ITS `trainable_weights` order; the tests rebuild them from `spec`, so
+    any disagreement between the two orders shows up as a numeric mismatch): kernels glorot-uniform, biases and
+    LayerNorm beta U(-0.1, 0.1), gamma U(0.9, 1.1), one draw sequence consumed tensor by tensor."""
+    rng = np.random.default_rng(seed)
+    chunks = []
+    for name, shape in spec:
+        n = int(np.prod(shape))
+        if name.endswith(".kernel"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            chunks.append(rng.uniform(-lim, lim, size=n))
+        elif name.endswith(".gamma"):
+            chunks.append(rng.uniform(0.9, 1.1, size=n))
+        else:
+            chunks.append(rng.uniform(-0.1, 0.1, size=n))
+    return np.concatenate(chunks).astype(np.float32)
+
+
+def sample_indices(n: int, k: int = 64) -> np.ndarray:
+    """Fixed positions at which the goldens keep gradient / weight entries of a tensor with n elements."""
+    return np.unique(np.linspace(0, n - 1, min(n, k)).astype(np.int64))
+
+
 class P:
     """View helper: P(flat, spec)['name'] -> tensor view with the right shape (keeps autograd graph)."""
 

@@ -67,7 +67,13 @@ class _Net:
 
     def load_weights(self, location: str) -> None:
         path = location if location.endswith(".npz") else location + ".npz"
-        self.set_flat(np.load(path)["flat"])
+        with np.load(path) as z:
+            offs, sizes = self.engine.layout(self.which)
+            if "offsets" in z.files and (list(z["offsets"]) != offs or list(z["sizes"]) != sizes):
+                raise ValueError(f"{path}: stored tensor layout does not match this network "
+                                 f"({len(z['sizes'])} tensors / {int(np.sum(z['sizes']))} parameters stored, "
+                                 f"{len(sizes)} / {sum(sizes)} expected): different architecture or a critic file")
+            self.set_flat(z["flat"])
 
     def __call__(self, *args, **kwargs):
         if self.which == 0:
@@ -205,7 +211,7 @@ class Agent:
             L.check(self.engine.lib.tpc_sample_categorical(self.engine.h, L.ptr(p), p.shape[0], p.shape[1],
                                                            self.sample_seed, self.episode_id0, self._draw, L.ptr(out),
                                                            self.engine.stream), "tpc_sample_categorical")
-            self._draw += 1
+            self._draw += 1      # one Philox draw index per decision
             bin_ids = out.cpu().numpy().view(HostTensor)
         return bin_ids, bins_mask, bins_probs
 
@@ -301,5 +307,10 @@ class Agent:
     def rollout(self, env, bufs: RolloutTensors, greedy=None):
         """T steps of act -> env.step on device (trainer.py:49-100 / tester.py:173-209)."""
         greedy = (not self.stochastic_action_selection) if greedy is None else greedy
-        self.engine.rollout(env._cfg_struct(), bufs, greedy, self.sample_seed, env.episode_id0, self._draw)
-        self._draw += 1
+        # the kernel uses draw index epoch * T + t (net.cu): advance the shared counter by whole rollouts of THIS
+        # length so that neither a later rollout with another T nor step-wise act() calls can reuse a
+        # (seed, episode, draw) triple
+        T = bufs.R
+        epoch = -(-self._draw // T)
+        self.engine.rollout(env._cfg_struct(), bufs, greedy, self.sample_seed, env.episode_id0, epoch)
+        self._draw = (epoch + 1) * T

@@ -37,6 +37,7 @@ __device__ __forceinline__ float env_step_warp(const tpc_env_config& e, float* _
                                                float* __restrict__ mha_mask, float* __restrict__ is_empty, int b, int bin,
                                                int req, int N, int R, int lane) {
   const int S = N + R, F = e.num_features;
+  bin = min(max(bin, 0), S - 1);   // memory safety only: the host wrappers reject out-of-range ids (IndexError in the reference)
   float* st = batch + (size_t)b * S * F;
   float nodes[4], reqs[4], rem[4];
   bool eos = true;

@@ -390,7 +390,7 @@ __global__ void actor_loss_bwd_kernel(const float* __restrict__ logits, const in
   for (int j = lane; j < S; j += 32) sum += expf(l[j] - mx);
   sum = warp_sum(sum);
   const float lse = mx + logf(sum);
-  const int a = actions[i];
+  const int a = min(max(actions[i], 0), S - 1);   // host-supplied index: never read outside the row
   const float ad = adv[i];
   float ent = 0.f;
   for (int j = lane; j < S; j += 32) {

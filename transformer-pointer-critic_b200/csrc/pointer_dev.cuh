@@ -57,8 +57,11 @@ __device__ __forceinline__ int pointer_head(int c, const float* __restrict__ w1d
   sum = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) sum += red[w];
+  // NaN logits (diverged weights) compare false everywhere: threads that own a column start from it, the others
+  // from column 0 with a probability no real one can lose against, so the result is always inside [0, S) like
+  // tf.argmax's (which returns an in-range index for NaN rows too).
   float best = -1.f;
-  int besti = 0x7fffffff;
+  int besti = threadIdx.x < S ? threadIdx.x : 0;
   for (int j = threadIdx.x; j < S; j += 256) {
     const float p = sl[j] / sum;
     sl[j] = p;
@@ -77,7 +80,7 @@ __device__ __forceinline__ int pointer_head(int c, const float* __restrict__ w1d
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w)
       if (red[w] > best || (red[w] == best && redi[w] < besti)) { best = red[w]; besti = redi[w]; }
-    redi[0] = besti;
+    redi[0] = min(max(besti, 0), S - 1);
   }
   __syncthreads();
   return redi[0];

@@ -41,6 +41,9 @@ class _DeviceEnvBase:
         self.mask_nodes_in_mha = opts["mask_nodes_in_mha"]
         self.normalization_factor = opts["normalization_factor"]
         self.decimal_precision = opts["decimal_precision"]
+        if self.decimal_precision != 2:
+            # the kernels round with floor(x * 100 + 0.5) / 100 (misc/utils.py:19-22 at decimals = 2, every shipped config)
+            raise NotImplementedError(f"decimal_precision={self.decimal_precision}: only 2 is implemented on device")
         self.batch_size = opts["batch_size"]
         self.num_features = opts["num_features"]
         self.EOS_CODE = opts["EOS_CODE"]
@@ -138,8 +141,13 @@ class _DeviceEnvBase:
 
     def step(self, bin_ids, feasible_bin_mask):
         """env.py:115-203."""
-        ids = torch.as_tensor(np.asarray(bin_ids, dtype=np.int32)).to(self.device)
+        ids_h = np.asarray(bin_ids, dtype=np.int32).reshape(-1)
         B = self.batch_size
+        if ids_h.shape[0] != B:
+            raise ValueError(f"step() expects one bin id per episode ({B}), got {ids_h.shape[0]}")
+        if ids_h.size and (ids_h.min() < -self.tensor_size or ids_h.max() >= self.tensor_size):
+            raise IndexError(f"bin id out of bounds for axis 1 with size {self.tensor_size}")   # env.py:129 fancy index
+        ids = torch.as_tensor(np.where(ids_h < 0, ids_h + self.tensor_size, ids_h).astype(np.int32)).to(self.device)
         reward = torch.empty(B, dtype=torch.float32, device=self.device)
         e = self._cfg_struct()
         L.check(self.lib.tpc_env_step(self.h, C.byref(e), L.ptr(self.batch_d), L.ptr(self.bin_net_mask_d),
