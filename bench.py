@@ -72,37 +72,66 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(env_cfg, N, R, sample_states=256, rollout_steps=2):
-    from oracle.cpu_path import time_sample
-    r = time_sample(env_cfg, N, R, sample_states, rollout_steps)
+def dataflow_bytes_per_state(N, R, actor=(1, 128), critic=(3, 512), d=128):
+    """HBM bytes one stored state moves through the UPDATE in the current kernel decomposition,
+    counted in units of one [token, 128] fp32 row (512 B) per encoder token-layer with dff = m * 128:
+      forward  : QKV 1+3, attention 3+1, O-proj + LN 1+1+1, FFN1 1+m, FFN2 + LN m+1+1             = 14 + 2m
+      backward : 2 x LN 3, dW2 m+1, dH 1+m, dW1 1+m, d(out1) m+1+1, dWo 2, d(att) 2, attention 3+1+1+3, dWqkv 1+3,
+                 dx 3+1+1                                                                          = 32 + 4m
+    times (N + R) tokens x 2 (bins + resources stacks, then the joint stack) x layers, critic + actor (the actor's
+    decoder / pointer add (2 * 3 + 3 * 3) rows per token once). The rollout adds one actor forward per decision."""
+    S = N + R
+    u = d * 4
+    total = 0
+    for layers, dff in (critic, actor):
+        m = dff // d
+        total += 2 * S * layers * ((14 + 2 * m) + (32 + 4 * m)) * u
+    total += S * 15 * u                                   # K2|V2|W2 projection of the decoder, forward + backward
+    m = actor[1] // d
+    rollout = 2 * S * actor[0] * (14 + 2 * m) * u + S * 4 * u
+    return total, rollout
+
+
+CPU_EPISODES = 32
+
+
+def cpu_sample_text(N, R, episodes):
+    return (f"one COMPLETE training iteration at {N - 1} nodes x {R} rules with batch {episodes} instead of 1024: "
+            f"{R}-step rollout of {episodes} episodes (actor forward per step), returns, one critic and one actor "
+            f"forward/backward over the {R * episodes} stored states, both Adam steps (torch-CPU fp32 oracle port, all "
+            f"host threads); decisions/s = {R * episodes} / wall time")
+
+
+def cpu_baseline(env_cfg, N, R, episodes=CPU_EPISODES):
+    from oracle.cpu_path import time_full_iteration
+    r = time_full_iteration(env_cfg, N, R, episodes)
     return {"value": r["decisions_per_s"], "unit": "decisions/s", "cores": r["threads"], "kind": "port",
-            "sample": f"{rollout_steps} rollout steps + 1 critic/actor forward-backward-Adam on {sample_states} states "
-                      f"at {N - 1} nodes x {R} rules (torch-CPU fp32 oracle port, extrapolated per decision)"}
+            "sample": cpu_sample_text(N, R, episodes), "rollout_s": r["t_rollout_s"], "update_s": r["t_update_s"]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    _, env_cfg = load_cfg(WORKLOAD["batch_per_gpu"], WORKLOAD["nodes"], WORKLOAD["rules"])
-    N, R = WORKLOAD["nodes"] + 1, WORKLOAD["rules"]
-    from oracle.cpu_path import time_sample
+    _, env_cfg = load_cfg(WORKLOAD["batch_per_gpu"], args.nodes, args.rules, args.reward)
+    N, R = args.nodes + 1, args.rules
+    from oracle.cpu_path import time_full_iteration
     for _ in range(args.warmup):
-        time_sample(env_cfg, N, R, 16, 1)
+        time_full_iteration(env_cfg, N, R, 2)
     vals, t0 = [], time.perf_counter()
     for _ in range(args.steps):
-        vals.append(time_sample(env_cfg, N, R, 256, 2))
+        vals.append(time_full_iteration(env_cfg, N, R, CPU_EPISODES))
     wall = time.perf_counter() - t0
     v = statistics.mean(x["decisions_per_s"] for x in vals)
     cores = vals[0]["threads"]
-    sample = "per step: 2 rollout steps + critic/actor forward-backward-Adam on 256 states at 50 nodes x 100 rules"
+    sample = "per step: " + cpu_sample_text(N, R, CPU_EPISODES)
     print(json.dumps({
         "impl": "reference", "metric": "ResourceV3 placement decisions/sec (rollout+A2C update)", "value": v,
         "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ResourceV3 {WORKLOAD['nodes']} nodes x {WORKLOAD['rules']} rules, batch "
-                               f"{WORKLOAD['batch_per_gpu']}/GPU, greedy reward, rollout + A2C update (actor 1 layer, "
+        "config": {"workload": f"ResourceV3 {args.nodes} nodes x {args.rules} rules, batch "
+                               f"{WORKLOAD['batch_per_gpu']}/GPU, {args.reward} reward, rollout + A2C update (actor 1 layer, "
                                f"critic 3 layers)", "timing": sample},
         "cpu_baseline": {"value": v, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -135,7 +164,77 @@ def roofline_probe(lib, h, st, M, dev):
     return call, alg_bytes, "FFN2 512->128 3xTF32 + residual + LayerNorm"
 
 
+def run_check(args, world, rank, dev, B, nodes, rules):
+    """Multi-GPU correctness: every rank rolls out its shard of the GLOBAL batch (episode ids rank*B ...),
+    runs the overlapped update (critic all-reduce behind the actor tape) and keeps the all-reduced gradients; rank 0
+    then repeats the iteration alone on the full global batch from the same parameters. Asserted: actions and rewards
+    bit-identical for any rank count, all-reduced gradients equal to the full-batch gradients (norm-wise), losses equal.
+    Prints one JSON line with the measured differences."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tpc_b200 import lib as L
+    from tpc_b200.agent import Agent
+    from tpc_b200.env import ResourceEnvironmentV3
+
+    def one_pass(batch, id0, ws, allreduce):
+        agent_cfg, env_cfg = load_cfg(batch, nodes, rules, args.reward)
+        env = ResourceEnvironmentV3("ResourceV3", env_cfg, dev)
+        env.add_stats_to_agent_config(agent_cfg)
+        agent = Agent("transformer", agent_cfg, dev, num_features=3, seed=0)
+        env.episode_id0 = agent.episode_id0 = id0
+        bufs = env.device_buffers(store=True)
+        env.reset_into(bufs)
+        agent.rollout(env, bufs)
+        eng = agent.engine
+        hyper = (agent.gamma, agent.values_loss_coefficient, agent.entropy_coefficient)
+        total = batch * ws * bufs.R
+        if allreduce is None:
+            eng.a2c_grads(bufs, *hyper, total_states=total)
+        else:
+            eng.a2c_grads(bufs, *hyper, total_states=total, phases=L.A2C_CRITIC)
+            w1 = allreduce(eng.grads[1])
+            eng.a2c_grads(bufs, *hyper, total_states=total, phases=L.A2C_ACTOR)
+            for w in (w1, allreduce(eng.grads[0]), allreduce(eng.losses)):
+                w.wait()
+        torch.cuda.synchronize()
+        return (bufs.actions.clone(), bufs.rewards.clone(), eng.grads[0].clone(), eng.grads[1].clone(),
+                (eng.losses / float(total)).clone(), eng.layout(0), eng.layout(1))
+
+    ar = (lambda t: dist.all_reduce(t, async_op=True)) if world > 1 else None
+    acts, rews, ga, gc, losses, _, _ = one_pass(B, rank * B, world, ar)
+    if world > 1:
+        all_a = [torch.empty_like(acts) for _ in range(world)]
+        all_r = [torch.empty_like(rews) for _ in range(world)]
+        dist.all_gather(all_a, acts)
+        dist.all_gather(all_r, rews)
+        acts, rews = torch.cat(all_a, dim=1), torch.cat(all_r, dim=0)
+    if rank == 0:
+        fa, fr, fga, fgc, flosses, la, lc = one_pass(B * world, 0, 1, None)
+
+        def per_tensor(g, ref, layout):
+            worst = 0.0
+            for o, n in zip(*layout):
+                nr = float(ref[o:o + n].norm())
+                if nr > 1e-6 * float(ref.norm()):
+                    worst = max(worst, float((g[o:o + n] - ref[o:o + n]).norm()) / nr)
+            return worst
+        res = {"check": "multi_gpu", "n_gpus": world, "global_batch": B * world, "nodes": nodes, "rules": rules,
+               "actions_equal": bool(torch.equal(acts, fa)), "rewards_equal": bool(torch.equal(rews, fr)),
+               "actor_grad_rel": per_tensor(ga, fga, la), "critic_grad_rel": per_tensor(gc, fgc, lc),
+               "loss_rel": float(((losses - flosses).abs() / flosses.abs().clamp_min(1e-12)).max())}
+        res["ok"] = bool(res["actions_equal"] and res["rewards_equal"] and res["actor_grad_rel"] < 1e-4
+                         and res["critic_grad_rel"] < 1e-4 and res["loss_rel"] < 1e-5)
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not res["ok"]:
+        raise SystemExit(1)
+
+
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from tpc_b200 import lib as L
@@ -151,6 +250,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, nodes, rules = args.batch or WORKLOAD["batch_per_gpu"], args.nodes, args.rules
+    if args.scaling == "strong":
+        # total work fixed: the GLOBAL batch (default 1024) is split over the ranks
+        gb = args.global_batch or WORKLOAD["batch_per_gpu"]
+        if gb % world:
+            raise SystemExit(f"--global-batch {gb} is not divisible by {world} ranks")
+        B = gb // world
+    if args.check:
+        return run_check(args, world, rank, dev, B, nodes, rules)
     agent_cfg, env_cfg = load_cfg(B, nodes, rules, args.reward)
     env = ResourceEnvironmentV3("ResourceV3", env_cfg, dev)
     env.add_stats_to_agent_config(agent_cfg)
@@ -201,8 +308,8 @@ def run_ours(args):
         bufs.batch.copy_(hb, non_blocking=True)
         bufs.bin_net_mask.zero_(); bufs.bin_net_mask[:, N:] = 1.0; bufs.mha_mask.zero_()
         agent.rollout(env, bufs)
-        lo = agent.update(bufs, world_size=world, allreduce=(lambda t: dist.all_reduce(t)) if world > 1 else None,
-                          chunk_states=args.chunk)
+        lo = agent.update(bufs, world_size=world, chunk_states=args.chunk,
+                          allreduce=(lambda t: dist.all_reduce(t, async_op=True)) if world > 1 else None)
         host_out[:B].copy_(bufs.rewards.sum(dim=1), non_blocking=True)
         host_out[B:].copy_(lo, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -219,7 +326,6 @@ def run_ours(args):
         return
 
     # ---------------- roofline of the dominant kernel (gemm_tc_kernel), measured live with CUDA events
-    import ctypes as C
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -250,21 +356,35 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # tensor-core view of the whole step: dense algorithmic FLOPs per decision x decisions/s per GPU against
+    # a tcgen05 kind::tf32 peak measured right here (resident operands, every SM issuing: tpc_tf32_peak_probe)
+    tf32 = C.c_float(0.0)
+    L.check(lib.tpc_tf32_peak_probe(h, 20000, C.byref(tf32), st), "tpc_tf32_peak_probe")
+    step_tflops = value / world * FLOP_PER_DECISION / 1e12 if (nodes, rules) == (50, 100) else None
+    tensor = {"bound": "tensor", "achieved": step_tflops, "peak": float(tf32.value), "unit": "TFLOP/s",
+              "frac": (step_tflops / float(tf32.value)) if step_tflops else None,
+              "peak_source": "measured live: tcgen05.mma kind::tf32 M128 N256 K8, operands resident in shared memory, "
+                             "148 CTAs (tpc_tf32_peak_probe); 3xTF32 forward GEMMs issue 3 MMAs per algorithmic one",
+              "flop_per_decision": FLOP_PER_DECISION}
     roofline = {"bound": "hbm", "achieved": alg_bytes / t_gemm / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / t_gemm / 1e9 / hbm_peak, "traffic": traffic,
                 "kernel": f"gemm_tc_kernel ({label}, M={M}, {t_gemm * 1e6:.1f} us/launch)",
-                "peak_source": peak_src,
-                "step_tensor_tflops": value / world * FLOP_PER_DECISION / 1e12 if (nodes, rules) == (50, 100) else None}
+                "peak_source": peak_src, "step_tensor_tflops": step_tflops, "tensor": tensor}
 
     cpu = cpu_baseline(env_cfg, N, R) if world == 1 and not args.no_cpu else None
     out = {
         "metric": "ResourceV3 placement decisions/sec (rollout+A2C update)", "value": value, "unit": "decisions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 forward, TF32 backward)",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32 (3xTF32 forward, TF32 backward)",
         "data": "synthetic",
         "config": {"workload": f"ResourceV3 {nodes} nodes x {rules} rules, batch {B}/GPU, {args.reward} reward, rollout + A2C "
                                f"update (actor 1 layer, critic 3 layers)",
                    "decisions_per_step": world * B * T, "chunk_states": chunk,
+                   "hbm_bytes_per_state": {"update": dataflow_bytes_per_state(N, R)[0],
+                                           "rollout": dataflow_bytes_per_state(N, R)[1],
+                                           "note": "modelled from the kernel decomposition (bench.py "
+                                                   "dataflow_bytes_per_state), not a counter"},
                    "l2": "working set per step (>4 GB of activations) far exceeds the 126 MB L2; no flush needed",
                    "parallelism": f"dp{world}"},
         "clocks": clocks,
@@ -291,6 +411,12 @@ def main():
     ap.add_argument("--rules", type=int, default=WORKLOAD["rules"])
     ap.add_argument("--chunk", type=int, default=0, help="states per update chunk (default: ~10240, equal chunks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch episodes per GPU; strong: --global-batch episodes split over the ranks")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total episodes (default 1024)")
+    ap.add_argument("--check", action="store_true",
+                    help="multi-GPU correctness instead of timing: N-rank gradients + all-reduce vs the 1-rank "
+                         "full-batch gradient, trajectories independent of the rank count")
     ap.add_argument("--reward", default="greedy", help="ResourceV3 reward type (BASELINE config #3: global_dominant = "
                     "fair, reduced_node_usage = cost); the headline metric is quoted on greedy")
     args = ap.parse_args()

@@ -187,7 +187,12 @@ typedef struct tpc_a2c_hyper {
   float gamma, values_loss_coefficient, entropy_coefficient;  /* agents/agent.py:31-33 */
   int chunk_states;       /* states per forward/backward chunk (0 = default) */
   int total_states;       /* T*B of the WHOLE job (all ranks): denominator of both mean losses */
+  int phases;             /* 0 = critic then actor (trainer.py:115-141); TPC_A2C_CRITIC / TPC_A2C_ACTOR run one tape only,
+                             so that the caller can start the critic-gradient all-reduce while the actor tape runs.
+                             The actor phase reads the `advantages` the critic phase wrote. */
 } tpc_a2c_hyper;
+#define TPC_A2C_CRITIC 1
+#define TPC_A2C_ACTOR 2
 
 /* compute_discounted_rewards + compute_value_loss + compute_actor_loss + both GradientTapes
  * (agents/agent.py:110-242, agents/trainer.py:103-141). Gradients are ACCUMULATED into actor_grads /
@@ -197,6 +202,19 @@ int tpc_a2c_grads(tpc_model* m, const float* actor_shadow, const float* actor_pa
                   const float* critic_params, const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources,
                   const tpc_a2c_hyper* hp, float* actor_grads, float* critic_grads, float* values, float* advantages,
                   float* losses, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Zero `nbytes` of device memory on `stream` (gradient / loss accumulators before tpc_a2c_grads; the reference's tapes
+ * start from fresh tensors, agents/trainer.py:115,125). */
+int tpc_zero(tpc_handle* h, void* ptr, size_t nbytes, void* stream);
+
+/* out[i] = in[i] * scale, n small (the 4 loss sums -> means: value_loss / mean(policy_loss) / bin_loss /
+ * mean(entropy) of agents/trainer.py:159-162). in == out is allowed. */
+int tpc_scale(tpc_handle* h, const float* in, int n, float scale, float* out, void* stream);
+
+/* Roofline denominator for the projection GEMMs ("measure a tcgen05 kind::tf32 GEMM peak"):
+ * every SM issues `iters` x 4 tcgen05.mma kind::tf32 (M=128, N=256, K=8) on operands resident in shared memory, timed
+ * with CUDA events on `stream` (the call synchronises). *tflops_host = dense TF32 TFLOP/s at the clocks of that moment. */
+int tpc_tf32_peak_probe(tpc_handle* h, int iters, float* tflops_host, void* stream);
 
 /* Keras Adam with per-variable clipnorm (agents/agent.py:39-49): clipnorm <= 0 disables it.
  * step is 1-based. grad_scale multiplies the gradients first (1/world_size after a sum all-reduce). */

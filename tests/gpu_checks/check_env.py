@@ -208,6 +208,68 @@ def check_rollout_and_adam():
     eng.close()
 
 
+def check_config2_corner(nodes, rules, B=1024, n_check=16, reward="greedy"):
+    """BASELINE config #2 at its own size: greedy decode of a batch-1024 tester cell on the device (fused rollout),
+    then `n_check` of those episodes (spread over the batch, addressed by their global episode ids) are replayed
+    through the oracle environment and the oracle actor: stored states / masks / rewards bit-exact, logits within
+    1e-3, and every pick equal to the oracle's argmax wherever the oracle's top-2 logit margin exceeds 1e-3."""
+    rng = np.random.default_rng(nodes * 1000 + rules)
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "env_rv3_shipped_greedy.json")))
+    cfg["reward"]["type"] = reward
+    cfg.update(batch_size=B, node_sample_size=nodes, profiles_sample_size=rules)
+    N, R, F = nodes + 1, rules, 3
+    S = N + R
+    mc, ca, cc = make_cfg(N, R)
+    eng = Engine(mc, dev)
+    pa = om.init_params(om.actor_spec(ca), 5) + (rng.standard_normal(eng.n_params[0]) * 0.02).astype(np.float32)
+    eng.set_params(0, pa)
+    e = env_config_struct(cfg, 0)
+    prof = torch.empty(cfg["num_profiles"], F, device=dev)
+    L.check(eng.lib.tpc_env_generate_profiles(eng.h, C.byref(e), 1235, L.ptr(prof), eng.stream))
+    bufs = RolloutTensors(B, N, R, F, dev, keep_logits=True)
+    L.check(eng.lib.tpc_env_reset(eng.h, C.byref(e), 1235, 0, 3, L.ptr(prof), B, N, R, L.ptr(bufs.batch),
+                                  L.ptr(bufs.bin_net_mask), L.ptr(bufs.mha_mask), L.ptr(bufs.is_empty), eng.stream))
+    init = bufs.batch.cpu().numpy().copy()
+    eng.rollout(e, bufs, True, 99, 0, 0)
+    torch.cuda.synchronize()
+    ids = np.unique(np.linspace(0, B - 1, n_check).astype(int))
+    n = len(ids)
+    sub = dict(cfg)
+    sub["batch_size"] = n
+    env = ResourceV3Oracle(sub)
+    state, dec, bm, mh = env.load(init[ids])
+    acts = bufs.actions.cpu().numpy()[:, ids]
+    states, pms, mhs = (x.cpu().numpy()[:, ids] for x in (bufs.states, bufs.ptr_masks, bufs.mha_masks))
+    logits, rewards = bufs.logits.cpu().numpy()[:, ids], bufs.rewards.cpu().numpy()[ids]
+    fa = torch.tensor(pa)
+    agree = bad = 0
+    worst = 0.0
+    for t in range(R):
+        feas = env.build_feasible_mask(state, dec, bm)
+        assert bits_equal(states[t], state[:, :, :F]), (t, "states")
+        assert bits_equal(pms[t], feas), (t, "feasible")
+        assert bits_equal(mhs[t], mh.reshape(n, S)), (t, "mha")
+        ol, op, oi = om.actor_forward(fa, ca, torch.tensor(state), torch.tensor(dec), torch.tensor(feas),
+                                      torch.tensor(mh), N)
+        ol = ol.numpy()
+        unm = feas == 0
+        worst = max(worst, float(np.abs(logits[t][unm] - ol[unm]).max() / np.abs(ol[unm]).max()))
+        srt = np.sort(np.where(unm, ol, -np.inf), axis=1)
+        margin = srt[:, -1] - srt[:, -2]
+        same = acts[t] == oi.numpy()
+        agree += int(same.sum())
+        bad += int(((~same) & (margin > 1e-3 * np.abs(srt[:, -1]).clip(1e-3))).sum())
+        state, dec, rw, done, info = env.step(acts[t], feas)
+        assert bits_equal(rewards[:, t], np.asarray(rw, dtype=np.float32).reshape(n)), (t, "reward")
+        bm, mh = info["bin_net_mask"], info["mha_used_mask"]
+    assert done and bits_equal(bufs.batch.cpu().numpy()[ids], state[:, :, :F])
+    print(f"config #2 cell {nodes} x {rules}, batch {B}: {n} episodes replayed bit-exact; logits rel err {worst:.2e}; "
+          f"picks equal {agree}/{n * R}, disagreements with margin > 1e-3: {bad}")
+    assert worst < 1e-3 and bad == 0
+    eng.close()
+    return worst
+
+
 def main():
     lib = L.load()
     h = C.c_void_p()

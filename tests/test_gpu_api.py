@@ -152,6 +152,14 @@ def test_full_size_rollout_properties(reward):
         assert torch.equal(bufs.rewards.sum(1), (R - rejected).float())
 
 
+@pytest.mark.parametrize("nodes,rules", [(5, 10), (50, 100)])
+def test_config2_corner_cells_replay_bit_exact_at_batch_1024(nodes, rules):
+    """BASELINE config #2 (tester sweep 5-50 nodes x 10-100 rules, greedy, batch 1024): the two corner cells, 16
+    episodes of each drawn out of the batch-1024 device rollout and replayed through the oracle (top-2-margin rule)."""
+    from tests.gpu_checks import check_env
+    check_env.check_config2_corner(nodes, rules, B=1024, n_check=16)
+
+
 def test_knapsack_v2_trains_on_the_same_kernels(tmp_path):
     """BASELINE config #4: configs/KnapsackV2.json (2 features, separate embeddings, clipnorm null)."""
     import torch

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.ModelConfig) == 16 * 4
     assert ctypes.sizeof(L.EnvConfig) == 15 * 4
     assert ctypes.sizeof(L.RolloutBuffers) == 12 * 8
-    assert ctypes.sizeof(L.A2CHyper) == 5 * 4
+    assert ctypes.sizeof(L.A2CHyper) == 6 * 4
 
 
 def test_get_configs_matches_reference_signature():

@@ -289,20 +289,30 @@ class Agent:
 
     def update(self, bufs: RolloutTensors, world_size: int = 1, allreduce=None, chunk_states: int = 0):
         """trainer.py:103-156 on device: returns, value loss, actor loss, both backward passes, both Adam steps.
-        `allreduce(tensor)` sums a device tensor over the data-parallel ranks (None for one process).
-        Returns the 4 reported scalars (value_loss, mean policy loss, total actor loss, mean entropy)."""
+        `allreduce(tensor)` starts a SUM over the data-parallel ranks and returns a handle with `.wait()` (or None
+        when it already completed); None for one process. The critic gradients are complete after the critic tape,
+        so their all-reduce runs on the communication stream while the actor tape computes; the actor
+        gradients and the 4 loss sums follow, and both Adam steps wait for the handles.
+        Returns the 4 reported scalars (value_loss, mean policy loss, total actor loss, mean entropy) on the device."""
         n_local = bufs.B * bufs.R
         total = n_local * world_size
-        self.engine.a2c_grads(bufs, self.gamma, self.values_loss_coefficient, self.entropy_coefficient,
-                              chunk_states=chunk_states, total_states=total)
-        losses = self.engine.losses
+        eng = self.engine
+        hyper = (self.gamma, self.values_loss_coefficient, self.entropy_coefficient)
         if allreduce is not None and world_size > 1:
-            allreduce(self.engine.grads[1])
-            allreduce(self.engine.grads[0])
-            allreduce(losses)
+            eng.a2c_grads(bufs, *hyper, chunk_states=chunk_states, total_states=total, phases=L.A2C_CRITIC)
+            pending = [allreduce(eng.grads[1])]
+            eng.a2c_grads(bufs, *hyper, chunk_states=chunk_states, total_states=total, phases=L.A2C_ACTOR)
+            pending += [allreduce(eng.grads[0]), allreduce(eng.losses)]
+            for w in pending:
+                if w is not None:
+                    w.wait()
+        else:
+            eng.a2c_grads(bufs, *hyper, chunk_states=chunk_states, total_states=total)
         self.critic_opt.apply_gradients()
         self.pointer_opt.apply_gradients()
-        return losses / float(total)
+        out = torch.empty(4, dtype=torch.float32, device=eng.device)
+        L.check(eng.lib.tpc_scale(eng.h, L.ptr(eng.losses), 4, 1.0 / float(total), L.ptr(out), eng.stream), "tpc_scale")
+        return out
 
     def rollout(self, env, bufs: RolloutTensors, greedy=None):
         """T steps of act -> env.step on device (trainer.py:49-100 / tester.py:173-209)."""

@@ -477,8 +477,10 @@ int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_p
   const size_t mark = ar.off;
   if (!ar.dry) TPC_TRY(discounted_returns(buf->rewards, B, T, hp->gamma, Rt, st));
   const bool cost = buf->is_empties != nullptr;
+  const bool do_critic = hp->phases == 0 || (hp->phases & TPC_A2C_CRITIC) || ar.dry;
+  const bool do_actor = hp->phases == 0 || (hp->phases & TPC_A2C_ACTOR) || ar.dry;
   // ---- critic: value loss + gradients (agents/agent.py:126-166, trainer.py:115-123)
-  for (long long s0 = 0; s0 < n; s0 += chunk) {
+  for (long long s0 = 0; do_critic && s0 < n; s0 += chunk) {
     const int C = (int)((n - s0) < chunk ? (n - s0) : chunk);
     ar.off = mark;
     Ctx cx = make_ctx(m, 1, critic_params, critic_shadow, critic_grads, &ar, stream);
@@ -492,7 +494,7 @@ int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_p
     if (ar.dry) break;
   }
   // ---- actor: policy loss (+ zero-gradient entropy term) and gradients (agents/agent.py:168-242, trainer.py:125-141)
-  for (long long s0 = 0; s0 < n; s0 += chunk) {
+  for (long long s0 = 0; do_actor && s0 < n; s0 += chunk) {
     const int C = (int)((n - s0) < chunk ? (n - s0) : chunk);
     ar.off = mark;
     Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, actor_grads, &ar, stream);

@@ -36,11 +36,85 @@ __global__ void __launch_bounds__(256) reward_stats_kernel(const float* __restri
     out[2] = sum / (float)B;
   }
 }
+
+__global__ void scale_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale;
+}
+
+// tcgen05.mma kind::tf32 issue rate on operands resident in shared memory: the ceiling of every projection GEMM
+// (one CTA per SM, thread 0 issues, 3 operand stages walked like the GEMM kernels do, accumulator in TMEM).
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (3 * 16384 + 3 * 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 256, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % 3;
+      const uint64_t da = umma_smem_desc_sw128(smem_u32(smem + st * 16384), 16, 1024);
+      const uint64_t db = umma_smem_desc_sw128(smem_u32(smem + 3 * 16384 + st * 32768), 16, 1024);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_tf32_ss(tm, da + 2 * kk, db + 2 * kk, idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
 }  // namespace
 
 extern "C" {
 
 unsigned long long tpc_launch_count(void) { return g_tpc_launches; }
+
+int tpc_zero(tpc_handle* h, void* ptr, size_t nbytes, void* stream) {
+  if (!h || (!ptr && nbytes)) return TPC_ERR_ARG;
+  if (nbytes) TPC_CHECK_CUDA(cudaMemsetAsync(ptr, 0, nbytes, (cudaStream_t)stream));
+  return TPC_OK;
+}
+
+int tpc_scale(tpc_handle* h, const float* in, int n, float scale, float* out, void* stream) {
+  if (!h || !in || !out || n < 0) return TPC_ERR_ARG;
+  if (n == 0) return TPC_OK;
+  scale_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, n, scale, out);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_tf32_peak_probe(tpc_handle* h, int iters, float* tflops_host, void* stream) {
+  if (!h || !tflops_host || iters < 1) return TPC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 3 * 16384 + 3 * 32768 + 2048;
+  TPC_CHECK_CUDA(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  TPC_CHECK_CUDA(cudaEventCreate(&e0));
+  TPC_CHECK_CUDA(cudaEventCreate(&e1));
+  tf32_peak_kernel<<<h->num_sms, 128, smem, st>>>(iters / 8 + 1);   // warm-up
+  TPC_CHECK_CUDA(cudaEventRecord(e0, st));
+  tf32_peak_kernel<<<h->num_sms, 128, smem, st>>>(iters);
+  TPC_CHECK_CUDA(cudaEventRecord(e1, st));
+  TPC_CHECK_CUDA(cudaEventSynchronize(e1));
+  g_tpc_launches += 2;
+  float ms = 0.f;
+  TPC_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  TPC_CHECK_CUDA(cudaGetLastError());
+  *tflops_host = (float)(2.0 * 128 * 256 * 8 * 4.0 * iters * h->num_sms / (ms * 1e-3) / 1e12);
+  return TPC_OK;
+}
 
 int tpc_create(tpc_handle** out) {
   if (!out) return TPC_ERR_ARG;

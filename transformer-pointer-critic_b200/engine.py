@@ -171,17 +171,20 @@ class Engine:
                                      ws.numel(), self.stream), "tpc_rollout")
 
     def a2c_grads(self, bufs: "RolloutTensors", gamma: float, c_v: float, c_e: float, chunk_states: int = 0,
-                  total_states: int = 0):
-        """Zeroes and fills self.grads[0/1]; returns (values, advantages) of the local T*B states."""
+                  total_states: int = 0, phases: int = 0):
+        """Zeroes and fills self.grads[0/1]; returns (values, advantages) of the local T*B states.
+        phases: 0 = both tapes; L.A2C_CRITIC, then L.A2C_ACTOR, run them as two calls (the second one reuses the
+        values / advantages of the first) so that a gradient all-reduce can start in between."""
         B, N, R = bufs.B, bufs.N, bufs.R
         n = B * R
-        hp = L.A2CHyper(gamma, c_v, c_e, chunk_states, total_states or n)
+        hp = L.A2CHyper(gamma, c_v, c_e, chunk_states, total_states or n, phases)
         ws = self.workspace(self.lib.tpc_a2c_workspace_bytes(self.m, B, N, R, chunk_states))
-        for g in self.grads:
-            g.zero_()
-        self.losses.zero_()
-        values = torch.empty(n, dtype=torch.float32, device=self.device)
-        adv = torch.empty(n, dtype=torch.float32, device=self.device)
+        if phases != L.A2C_ACTOR:
+            for t in (self.grads[0], self.grads[1], self.losses):
+                L.check(self.lib.tpc_zero(self.h, L.ptr(t), t.numel() * 4, self.stream), "tpc_zero")
+            self._values = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._adv = torch.empty(n, dtype=torch.float32, device=self.device)
+        values, adv = self._values, self._adv
         rb = bufs.struct()
         L.check(self.lib.tpc_a2c_grads(self.m, L.ptr(self.shadow[0]), L.ptr(self.params[0]), L.ptr(self.shadow[1]),
                                        L.ptr(self.params[1]), C.byref(rb), B, N, R, C.byref(hp),

@@ -36,7 +36,10 @@ class RolloutBuffers(C.Structure):
 
 class A2CHyper(C.Structure):
     _fields_ = [("gamma", c_float), ("values_loss_coefficient", c_float), ("entropy_coefficient", c_float),
-                ("chunk_states", c_int), ("total_states", c_int)]
+                ("chunk_states", c_int), ("total_states", c_int), ("phases", c_int)]
+
+
+A2C_CRITIC, A2C_ACTOR = 1, 2
 
 
 ERRORS = {0: "TPC_OK", -1: "TPC_ERR_CUDA", -2: "TPC_ERR_ARG", -3: "TPC_ERR_SHAPE", -4: "TPC_ERR_WORKSPACE",
@@ -81,6 +84,9 @@ SIGNATURES = {
     "tpc_a2c_grads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(RolloutBuffers), c_int,
                               c_int, c_int, C.POINTER(A2CHyper), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
+    "tpc_zero": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tpc_scale": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "tpc_tf32_peak_probe": (c_int, [c_void_p, c_int, C.POINTER(c_float), c_void_p]),
     "tpc_adam_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                c_float, c_void_p]),
     "tpc_heuristic_dominant": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -33,7 +33,7 @@ def train_iteration(env, agent: Agent, bufs=None, chunk_states: int = 0):
         bufs = env.device_buffers(store=True)
     env.reset_into(bufs)
     agent.rollout(env, bufs)
-    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    allreduce = (lambda t: dist.all_reduce(t, async_op=True)) if world > 1 else None
     losses = agent.update(bufs, world_size=world, allreduce=allreduce, chunk_states=chunk_states)
     return bufs, losses
 
