@@ -111,6 +111,14 @@ def run_case(case, verbose=True):
             if verbose and k == 0:
                 worst = own[big[own]][int(np.argmax(e))]
                 print(f"    {name}: worst element error {e.max():.2e} x rms in {spec[worst][0]} (norm {ref_n[worst]:.2e}, max norm {ref_n.max():.2e})")
+        # the same update in chunks of ONE step: every chunk leaves out the rule tokens placed before its step
+        # (TokWin, csrc/kernels.cuh) -- losses and actor gradients must not move
+        full = [eng.grads[0].clone(), eng.losses.clone()]
+        agent.engine.a2c_grads(bufs, agent.gamma, agent.values_loss_coefficient, agent.entropy_coefficient,
+                               chunk_states=B)
+        torch.cuda.synchronize()
+        out[f"{tag}_window_grad_actor"] = float((eng.grads[0] - full[0]).norm() / full[0].norm())
+        out[f"{tag}_window_losses"] = float(((eng.losses - full[1]).abs() / full[1].abs().clamp_min(1e-12)).max())
         agent.critic_opt.apply_gradients()
         agent.pointer_opt.apply_gradients()
         torch.cuda.synchronize()

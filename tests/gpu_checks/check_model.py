@@ -157,7 +157,10 @@ def main():
             print(f"  losses: value {losses[0]/nT:.6f} vs {float(vl):.6f} | policy {losses[1]/nT:.6f} vs {float(pl.mean()):.6f} | total {losses[2]/nT:.6f} vs {float(tot):.6f} | entropy {losses[3]/nT:.6f} vs {float(ent.mean()):.6f}")
             for nm, got, ref in (("value", losses[0] / nT, float(vl)), ("policy", losses[1] / nT, float(pl.mean())),
                                  ("total", losses[2] / nT, float(tot)), ("entropy", losses[3] / nT, float(ent.mean()))):
-                worst[f"loss_{nm}_{N}_{R}_{chunk}"] = abs(got - ref) / max(abs(ref), 1e-12)
+                # the total is a signed mean of policy_loss * advantage (random advantages here): its error is
+                # measured against the magnitude of the terms, not against a sum that may cancel
+                scale = float((pl * oadv.detach().squeeze(-1)).abs().mean()) if nm == "total" else abs(ref)
+                worst[f"loss_{nm}_{N}_{R}_{chunk}"] = abs(got - ref) / max(abs(ref), scale, 1e-12)
             e_adv = rel(adv.cpu().numpy(), oadv.detach().numpy().ravel())
             print(f"  values/adv err {e_adv:.2e}")
             worst[f"grad_{N}_{R}_{chunk}"] = max(ptc[wc], pta[wa])

@@ -284,10 +284,10 @@ __device__ __forceinline__ void prefetch_rows(const float* __restrict__ src, int
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)r * ld + c4 * 4) : "memory");
   }
 }
-__device__ __forceinline__ void prefetch_mask(const float* __restrict__ src, int L, float* raw) {
+__device__ __forceinline__ void prefetch_mask(const float* __restrict__ src, int L, float* raw, int split, int gap) {
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(raw + j));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + j) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + (j < split ? j : j + gap)) : "memory");
   }
 }
 __device__ __forceinline__ void raw_row(const float* raw, int r, int L, float4 (&x)[4]) {
@@ -308,7 +308,7 @@ __device__ __forceinline__ void raw_row(const float* raw, int r, int L, float4 (
 template <bool PV3X, int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 5 ? 3 : 12 / NW) attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                           int mS, int m0, int L, int nitems, float* __restrict__ att,
-                                                          float* __restrict__ lse) {
+                                                          float* __restrict__ lse, int msplit, int mgap) {
   constexpr int FWD_WARPS = NW, FWD_THREADS = NW * 32;
   extern __shared__ float sm[];
   __shared__ unsigned nrm_bits[2][2];   // [item parity][Q, K]: largest squared row norm (non-negative floats order as uints)
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 5 ? 3 : 12 / NW) attn_fwd_kerne
     const float* base = qkv + (size_t)c * L * 384 + hg;
 #pragma unroll
     for (int m = 0; m < 3; ++m) prefetch_rows(base + m * 128, 384, L, raw + m * Lp * RS);
-    prefetch_mask(mask + (size_t)c * mS + m0, L, Mraw);
+    prefetch_mask(mask + (size_t)c * mS + m0, L, Mraw, msplit, mgap);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (tid < 4) (&nrm_bits[0][0])[tid] = 0u;
@@ -654,7 +654,7 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ att,
                                                                    const float* __restrict__ lse, const float* __restrict__ datt,
                                                                    const float* __restrict__ mask, int mS, int m0, int L,
-                                                                   int pf_dist, float* __restrict__ dqkv) {
+                                                                   int pf_dist, float* __restrict__ dqkv, int msplit, int mgap) {
   extern __shared__ float sm[];
   __shared__ unsigned nrm_bits[4];          // largest squared row norm of Q, K, V, dO
   __shared__ unsigned long long live_bits_s;
@@ -691,7 +691,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
   float nq = 0.f, nk = 0.f, nv = 0.f, ng = 0.f;
   if (single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, 0, L, hg, h, d);
   if (tid < 4) nrm_bits[tid] = 0u;
-  for (int j = tid; j < Lr; j += BWD_THREADS) S.Ms[j] = j < L ? mask[(size_t)c * mS + m0 + j] * -BIG_NUMBER : -INFINITY;
+  for (int j = tid; j < Lr; j += BWD_THREADS)
+    S.Ms[j] = j < L ? mask[(size_t)c * mS + m0 + (j < msplit ? j : j + mgap)] * -BIG_NUMBER : -INFINITY;
   for (int row0 = 0; row0 < Lr; row0 += 4 * BWD_RPP) {
     if (!single) bwd_load_chunk<BWD_RPP>(base, obase, dobase, lse_c, row0, L, hg, h, d);
 #pragma unroll
@@ -822,7 +823,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 5 ? 3 : 16 / NW)) attn_bwd_ker
 }  // namespace
 
 int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
-                  cudaStream_t st) {
+                  cudaStream_t st, int mask_split, int mask_gap) {
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 512) return TPC_ERR_SHAPE;
   const int Lp = ((L + 7) / 8) * 8, Lr = (Lp + 15) & ~15, nt = Lp / 8;
@@ -848,19 +849,20 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
   }
   const int nitems = C * 8;
   const int grid = nitems < num_sms * ctas_per_sm[v] ? nitems : num_sms * ctas_per_sm[v];
-  kern<<<grid, nw * 32, smem, st>>>(qkv, mask, mS, m0, L, nitems, att, lse);
+  kern<<<grid, nw * 32, smem, st>>>(qkv, mask, mS, m0, L, nitems, att, lse, mask_split, mask_gap);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
 
 int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
-                  int m0, int C, int L, float* dqkv, cudaStream_t st) {
+                  int m0, int C, int L, float* dqkv, cudaStream_t st, int mask_split, int mask_gap) {
   if (C <= 0) return TPC_OK;
   if (L < 1 || L > 512) return TPC_ERR_SHAPE;
   const int Lr = (L + 15) & ~15;
   const size_t smem = (size_t)(4 * Lr * 8 + 3 * 16 * ts_stride(Lr) + 2 * (Lr / 8) * 16 + 3 * Lr + Lr / 16 + 8) * sizeof(float);
   const int nblk = Lr / 16, nw = nblk >= 9 ? 5 : (nblk + 1) / 2, v = nw - 1;
-  using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, int, int, int, int, float*);
+  using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, int, int, int, int, float*,
+                        int, int);
   static const Kern kerns[5] = {attn_bwd_kernel<1>, attn_bwd_kernel<2>, attn_bwd_kernel<3>, attn_bwd_kernel<4>,
                                 attn_bwd_kernel<5>};
   static size_t attr_smem[5] = {0, 0, 0, 0, 0};
@@ -875,7 +877,7 @@ int attention_bwd(const float* qkv, const float* att, const float* lse, const fl
     if (per_sm < 1) return TPC_ERR_SHAPE;
     resident[v] = sms * per_sm;
   }
-  kerns[v]<<<C * 8, nw * 32, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, resident[v], dqkv);
+  kerns[v]<<<C * 8, nw * 32, smem, st>>>(qkv, att, lse, datt, mask, mS, m0, L, resident[v], dqkv, mask_split, mask_gap);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

@@ -24,10 +24,13 @@ __global__ void __launch_bounds__(256) decide_step_kernel(const DecideArgs a) {
   const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.N + a.R, F = a.env.num_features;
 
-  const int best = pointer_head(c, a.w1d, a.kvw, a.V, a.bV, a.clipC, a.has_clip, a.ptr_mask, S, a.score, a.logits,
-                                nullptr, sl, red, redi);
+  const int Sc = S - a.win.gap;   // compact tokens (the window leaves out rules placed at earlier steps)
+  const int best = pointer_head(c, a.w1d, a.kvw, a.V, a.bV, a.clipC, a.has_clip, a.ptr_mask, Sc, a.score, a.logits,
+                                nullptr, sl, red, redi, a.win);
   if (threadIdx.x == 0) {
-    const int pick = a.greedy ? best : sample_pick(sl, S, a.seed, a.id0 + c, a.draw);
+    // the draw runs over the compact probabilities: the tokens left out have probability exactly 0, so the inverse-CDF
+    // pick over the full row is the same token
+    const int pick = a.greedy ? best : a.win.full(sample_pick(sl, Sc, a.seed, a.id0 + c, a.draw));
     a.actions[c] = pick;
     pick_s = pick;
   }

@@ -1,6 +1,7 @@
 // Fused per-step decision kernel of the rollout (decide.cu).
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace tpc {
 
@@ -11,6 +12,7 @@ struct DecideArgs {
   int has_clip;
   const float* ptr_mask;   // feasible mask of THIS step (C, S)
   float *score, *logits;   // optional outputs
+  TokWin win;              // compact token window of kvw (rule tokens placed at earlier steps are left out)
   // pick
   int greedy;
   uint64_t seed;

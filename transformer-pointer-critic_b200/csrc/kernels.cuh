@@ -9,6 +9,15 @@ namespace tpc {
 // compact row r of a stack with L tokens per state  <->  token (r / L) * S + s0 + (r % L) of the (.., S, ..) tensor.
 struct RowMap { int L, S, s0; };
 
+// Token window of the ACTOR's compact buffers. The first `gap` rule tokens of every state in the batch (rules placed
+// at earlier steps) are masked as attention keys in every stack and as pointer targets, and their own encoder rows are
+// only read by pointer logits that are masked anyway, so the actor leaves them out: exact. Compact token
+// j of a state <-> token (j < N ? j : j + gap) of the full (.., Sfull, ..) tensors (state, masks, logits).
+struct TokWin {
+  int N = 1 << 30, gap = 0, Sfull = 0;
+  __host__ __device__ int full(int j) const { return j < N ? j : j + gap; }
+};
+
 // out[r][0:128] = x[tok(r)][0:F] @ W[F][128] + b ; x has ldx floats per token; feature f == ldx is read from
 // `extra[tok]` when extra != nullptr (is_empty column of the "cost" reward state, env.py:424-426).
 // Restates the Dense / TimeDistributed(Dense) embeddings (common/encoder.py:101-121, actor/decoder.py:74).
@@ -33,16 +42,18 @@ int scatter_rows(const float* src, int rows, RowMap map, float* dst, cudaStream_
 // Self-attention of one encoder stack (common/attention.py:37-48 + common/utils.py:31-45) on packed
 // qkv[rows][384] (q | k | v), rows = C * L; mask[(c * mS) + m0 + j] != 0 hides key j.
 // att[rows][128] (heads merged), lse[rows][8] = log-sum-exp of the scaled masked logits (saved for backward).
+// mask_split / mask_gap: key j reads mask[c * mS + m0 + (j < mask_split ? j : j + mask_gap)] (TokWin of the joint stack)
 int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, int L, float* att, float* lse,
-                  cudaStream_t st);
+                  cudaStream_t st, int mask_split = 1 << 30, int mask_gap = 0);
 // dqkv[rows][384] from datt[rows][128]
 int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
-                  int m0, int C, int L, float* dqkv, cudaStream_t st);
+                  int m0, int C, int L, float* dqkv, cudaStream_t st, int mask_split = 1 << 30, int mask_gap = 0);
 
 // Decoder cross attention with ONE query per state (actor/decoder_layer.py:26-27): q2[C][128],
 // kvw[C*S][384] (K2 | V2 | W2e), mask[C][S] -> ctx[C][128], probs pc[C][8][S]
+// S = compact tokens per state; the mask row of state c is mask[c * w.Sfull + w.full(j)] (w.Sfull == 0: S, identity)
 int cross_attn_fwd(const float* q2, const float* kvw, const float* mask, int C, int S, float* ctx, float* pc,
-                   cudaStream_t st);
+                   cudaStream_t st, TokWin w = TokWin());
 // dq2[C][128], dkvw[:, 0:256]
 int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const float* pc, int C, int S, float* dq2,
                    float* dkvw, cudaStream_t st);
@@ -51,11 +62,11 @@ int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const f
 // score (pre-clip), logits (= C*tanh(score) - mask*1e9), probs = softmax(logits), argmax(probs).
 int pointer_fwd(const float* w1d, const float* kvw, const float* V, const float* bV, float clipC, int has_clip,
                 const float* ptr_mask, int C, int S, float* score, float* logits, float* probs, int32_t* argmax,
-                cudaStream_t st);
+                cudaStream_t st, TokWin w = TokWin());
 // dlogits[C][S] -> dw1d[C][128], dkvw[:, 256:384], dV[128] += , dbV +=
 int pointer_bwd(const float* dlogits, const float* score, const float* w1d, const float* kvw, const float* V,
                 float clipC, int has_clip, int C, int S, float* dw1d, float* dkvw, float* dV, float* dbV,
-                cudaStream_t st);
+                cudaStream_t st, TokWin w = TokWin());
 
 // value head tail (critic/model.py:81-83): v[c] = h1[c] . Wv + bv
 int value_head_fwd(const float* h1, const float* Wv, const float* bv, int C, float* v, cudaStream_t st);

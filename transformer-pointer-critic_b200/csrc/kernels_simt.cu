@@ -133,7 +133,7 @@ constexpr int XA_MAX_S = 512;
 
 __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __restrict__ q2, const float* __restrict__ kvw,
                                                              const float* __restrict__ mask, int S,
-                                                             float* __restrict__ ctx, float* __restrict__ pc) {
+                                                             float* __restrict__ ctx, float* __restrict__ pc, TokWin w) {
   __shared__ float ps[8][XA_MAX_S];
   const int c = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* kv = kvw + (size_t)c * S * 384;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __rest
       s = fmaf(q[d4 * 4 + 0], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
       s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
     }
-    s = s * 0.25f + mask[(size_t)c * S + j] * -BIG_NUMBER;  // / sqrt(16), + mask * -1e9 (common/utils.py:34-38)
+    s = s * 0.25f + mask[(size_t)c * (w.Sfull > 0 ? w.Sfull : S) + w.full(j)] * -BIG_NUMBER;  // / sqrt(16), + mask * -1e9 (common/utils.py:34-38)
     ps[h][j] = s;
     mx = fmaxf(mx, s);
   }
@@ -239,12 +239,12 @@ __global__ void __launch_bounds__(256) pointer_fwd_kernel(const float* __restric
                                                           const float* __restrict__ V, const float* __restrict__ bV,
                                                           float clipC, int has_clip, const float* __restrict__ ptr_mask,
                                                           int S, float* __restrict__ score, float* __restrict__ logits,
-                                                          float* __restrict__ probs, int32_t* __restrict__ argmax) {
+                                                          float* __restrict__ probs, int32_t* __restrict__ argmax, TokWin w) {
   __shared__ float sl[XA_MAX_S];
   __shared__ float red[8];
   __shared__ int redi[8];
   const int c = blockIdx.x;
-  const int best = pointer_head(c, w1d, kvw, V, bV, clipC, has_clip, ptr_mask, S, score, logits, probs, sl, red, redi);
+  const int best = pointer_head(c, w1d, kvw, V, bV, clipC, has_clip, ptr_mask, S, score, logits, probs, sl, red, redi, w);
   if (threadIdx.x == 0 && argmax) argmax[c] = best;
 }
 
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) pointer_bwd_kernel(const float* __restric
                                                           const float* __restrict__ w1d, const float* __restrict__ kvw,
                                                           const float* __restrict__ V, float clipC, int has_clip, int S,
                                                           float* __restrict__ dw1d, float* __restrict__ dkvw,
-                                                          float* __restrict__ dV, float* __restrict__ dbV) {
+                                                          float* __restrict__ dV, float* __restrict__ dbV, TokWin w) {
   __shared__ float4 sw[8][32], sv[8][32];
   __shared__ float sb[8];
   const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) pointer_bwd_kernel(const float* __restric
   float ab = 0.f;
   for (int j = warp; j < S; j += 8) {
     const size_t row = (size_t)c * S + j;
-    float dsc = dlogits[row];
+    float dsc = dlogits[(size_t)c * (w.Sfull > 0 ? w.Sfull : S) + w.full(j)];
     if (has_clip) {
       const float t = tanhf(score[row]);
       dsc *= clipC * (1.f - t * t);
@@ -460,10 +460,10 @@ int scatter_rows(const float* src, int rows, RowMap map, float* dst, cudaStream_
 }
 
 int cross_attn_fwd(const float* q2, const float* kvw, const float* mask, int C, int S, float* ctx, float* pc,
-                   cudaStream_t st) {
+                   cudaStream_t st, TokWin w) {
   if (C <= 0) return TPC_OK;
   if (S > XA_MAX_S) return TPC_ERR_SHAPE;
-  cross_attn_fwd_kernel<<<C, 256, 0, st>>>(q2, kvw, mask, S, ctx, pc);
+  cross_attn_fwd_kernel<<<C, 256, 0, st>>>(q2, kvw, mask, S, ctx, pc, w);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
@@ -479,19 +479,19 @@ int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const f
 
 int pointer_fwd(const float* w1d, const float* kvw, const float* V, const float* bV, float clipC, int has_clip,
                 const float* ptr_mask, int C, int S, float* score, float* logits, float* probs, int32_t* argmax,
-                cudaStream_t st) {
+                cudaStream_t st, TokWin w) {
   if (C <= 0) return TPC_OK;
   if (S > XA_MAX_S) return TPC_ERR_SHAPE;
-  pointer_fwd_kernel<<<C, 256, 0, st>>>(w1d, kvw, V, bV, clipC, has_clip, ptr_mask, S, score, logits, probs, argmax);
+  pointer_fwd_kernel<<<C, 256, 0, st>>>(w1d, kvw, V, bV, clipC, has_clip, ptr_mask, S, score, logits, probs, argmax, w);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
 
 int pointer_bwd(const float* dlogits, const float* score, const float* w1d, const float* kvw, const float* V,
                 float clipC, int has_clip, int C, int S, float* dw1d, float* dkvw, float* dV, float* dbV,
-                cudaStream_t st) {
+                cudaStream_t st, TokWin w) {
   if (C <= 0) return TPC_OK;
-  pointer_bwd_kernel<<<C, 256, 0, st>>>(dlogits, score, w1d, kvw, V, clipC, has_clip, S, dw1d, dkvw, dV, dbV);
+  pointer_bwd_kernel<<<C, 256, 0, st>>>(dlogits, score, w1d, kvw, V, clipC, has_clip, S, dw1d, dkvw, dV, dbV, w);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

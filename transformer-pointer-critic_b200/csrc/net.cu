@@ -8,6 +8,8 @@
 //   Decoder.call            actor/decoder.py:62-101        -> decoder_forward / decoder_backward
 //   CriticTransformer.call  critic/model.py:55-85          -> critic_forward / critic_backward
 //   trainer loop            agents/trainer.py:49-156       -> tpc_rollout / tpc_a2c_grads
+#include <vector>
+
 #include "model.cuh"
 #include "kernels.cuh"
 #include "env.cuh"
@@ -44,7 +46,7 @@ struct Ctx {
   int sms() const { return m->h->num_sms; }
 };
 
-struct MaskRef { const float* mask; int mS; int m0; };  // mask[c * mS + m0 + j]
+struct MaskRef { const float* mask; int mS; int m0; int split = 1 << 30; int gap = 0; };  // mask[c * mS + m0 + (j < split ? j : j + gap)]
 
 struct EncLayerActs {
   float *qkv, *lse, *att, *out1, *rstd1, *h, *out2, *rstd2;
@@ -122,7 +124,7 @@ int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int L
   const int rows = C * Lt, dff = cx.L->dff;
   alloc_layer(*cx.ar, a, rows, dff);
   TPC_TRY(gemm_fwd(cx, x, 128, cx.W + lp.s.wqkv_t, 128, a.qkv, 384, rows, 384, 128, epi_bias(cx.W + lp.s.bqkv)));
-  RUN(attention_fwd(a.qkv, mk.mask, mk.mS, mk.m0, C, Lt, a.att, a.lse, cx.st));
+  RUN(attention_fwd(a.qkv, mk.mask, mk.mS, mk.m0, C, Lt, a.att, a.lse, cx.st, mk.split, mk.gap));
   TPC_TRY(gemm_fwd(cx, a.att, 128, cx.W + lp.s.wo_t, 128, a.out1, 128, rows, 128, 128,
                epi_ln(cx, cx.P + lp.mha.o.b, x, lp.ln1, a.rstd1)));
   GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
@@ -161,23 +163,24 @@ int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int 
              cx.G + lp.ln1.b, cx.st));
   TPC_TRY(dense_grads(cx, a.att, 128, s.dA, 128, rows, lp.mha.o));
   TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.wo_c, 128, s.dB, 128, rows, 128, 128, GemmEpi()));          // datt
-  RUN(attention_bwd(a.qkv, a.att, a.lse, s.dB, mk.mask, mk.mS, mk.m0, C, Lt, s.dQKV, cx.st));
+  RUN(attention_bwd(a.qkv, a.att, a.lse, s.dB, mk.mask, mk.mS, mk.m0, C, Lt, s.dQKV, cx.st, mk.split, mk.gap));
   const DenseP* qkv[3] = {&lp.mha.q, &lp.mha.k, &lp.mha.v};
   TPC_TRY(fused_grads(cx, x, 128, s.dQKV, 384, rows, qkv, 3));
   TPC_TRY(gemm(cx, s.dQKV, 384, cx.W + lp.s.wqkv_c, 384, dx, 128, rows, 128, 384, epi_add(s.dA, 128)));  // dx
   return TPC_OK;
 }
 
-int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a) {
+// r0 > 0 (actor only): the first r0 rule tokens of every state are left out of the compact buffers (TokWin, kernels.cuh)
+int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a, int r0 = 0) {
   const NetLayout& L = *cx.L;
-  const int S = N + R, nl = L.nl;
+  const int S = N + R, nl = L.nl, Re = R - r0, Se = N + Re;
   Arena& ar = *cx.ar;
   a.emb_b = ar.f((size_t)C * N * 128);
-  a.emb_r = ar.f((size_t)C * R * 128);
+  a.emb_r = ar.f((size_t)C * Re * 128);
   const DenseP& eb = L.enc.emb1;
   const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
   RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, cx.P + eb.w, cx.P + eb.b, eb.in, a.emb_b, cx.st));
-  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * R, RowMap{R, S, N}, cx.P + er.w, cx.P + er.b, er.in, a.emb_r, cx.st));
+  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, cx.P + er.w, cx.P + er.b, er.in, a.emb_r, cx.st));
   a.bins.resize(nl); a.res.resize(nl); a.joint.resize(nl);
   const float* xb = a.emb_b;
   for (int i = 0; i < nl; ++i) {
@@ -186,15 +189,15 @@ int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, i
   }
   const float* xr = a.emb_r;
   for (int i = 0; i < nl; ++i) {
-    TPC_TRY(enc_layer_forward(cx, L.enc.res[i], xr, C, R, MaskRef{mha_mask, S, N}, a.res[i]));
+    TPC_TRY(enc_layer_forward(cx, L.enc.res[i], xr, C, Re, MaskRef{mha_mask, S, N + r0}, a.res[i]));
     xr = a.res[i].out2;
   }
-  a.cat = ar.f((size_t)C * S * 128);
-  RUN(scatter_rows(xb, C * N, RowMap{N, S, 0}, a.cat, cx.st));
-  RUN(scatter_rows(xr, C * R, RowMap{R, S, N}, a.cat, cx.st));
+  a.cat = ar.f((size_t)C * Se * 128);
+  RUN(scatter_rows(xb, C * N, RowMap{N, Se, 0}, a.cat, cx.st));
+  RUN(scatter_rows(xr, C * Re, RowMap{Re, Se, N}, a.cat, cx.st));
   const float* xj = a.cat;
   for (int i = 0; i < nl; ++i) {
-    TPC_TRY(enc_layer_forward(cx, L.enc.joint[i], xj, C, S, MaskRef{mha_mask, S, 0}, a.joint[i]));
+    TPC_TRY(enc_layer_forward(cx, L.enc.joint[i], xj, C, Se, MaskRef{mha_mask, S, 0, N, r0}, a.joint[i]));
     xj = a.joint[i].out2;
   }
   a.enc_out = const_cast<float*>(xj);
@@ -202,22 +205,23 @@ int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, i
 }
 
 // d_enc: gradient w.r.t. the encoder output [C*S,128] (overwritten as scratch)
-int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a, float* d_enc) {
+int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, int R, EncActs& a, float* d_enc,
+                     int r0 = 0) {
   const NetLayout& L = *cx.L;
-  const int S = N + R, nl = L.nl;
+  const int S = N + R, nl = L.nl, Re = R - r0, Se = N + Re;
   Arena& ar = *cx.ar;
   BwdScratch s;
-  s.dA = ar.f((size_t)C * S * 128);
-  s.dB = ar.f((size_t)C * S * 128);
-  s.dQKV = ar.f((size_t)C * S * 384);
-  float* dx0 = ar.f((size_t)C * S * 128);
-  float* dx1 = ar.f((size_t)C * S * 128);
+  s.dA = ar.f((size_t)C * Se * 128);
+  s.dB = ar.f((size_t)C * Se * 128);
+  s.dQKV = ar.f((size_t)C * Se * 384);
+  float* dx0 = ar.f((size_t)C * Se * 128);
+  float* dx1 = ar.f((size_t)C * Se * 128);
   const float* dcur = d_enc;
   float* dnext = dx0;
   for (int i = nl - 1; i >= 0; --i) {
     const float* x = i == 0 ? a.cat : a.joint[i - 1].out2;
-    TPC_TRY(enc_layer_backward(cx, L.enc.joint[i], x, C, S, MaskRef{mha_mask, S, 0}, a.joint[i], dcur,
-                               RowMap{S, S, 0}, dnext, s));
+    TPC_TRY(enc_layer_backward(cx, L.enc.joint[i], x, C, Se, MaskRef{mha_mask, S, 0, N, r0}, a.joint[i], dcur,
+                               RowMap{Se, Se, 0}, dnext, s));
     dcur = dnext;
     dnext = (dnext == dx0) ? dx1 : dx0;
   }
@@ -227,7 +231,7 @@ int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, 
   // bins stack
   {
     const float* dc = dcat;
-    RowMap dm{N, S, 0};
+    RowMap dm{N, Se, 0};
     float* bufs[2] = {other, third};
     int bi = 0;
     for (int i = nl - 1; i >= 0; --i) {
@@ -243,18 +247,18 @@ int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, 
   // resources stack
   {
     const float* dc = dcat;
-    RowMap dm{R, S, N};
+    RowMap dm{Re, Se, N};
     float* bufs[2] = {other, third};
     int bi = 0;
     for (int i = nl - 1; i >= 0; --i) {
       const float* x = i == 0 ? a.emb_r : a.res[i - 1].out2;
-      TPC_TRY(enc_layer_backward(cx, L.enc.res[i], x, C, R, MaskRef{mha_mask, S, N}, a.res[i], dc, dm, bufs[bi], s));
+      TPC_TRY(enc_layer_backward(cx, L.enc.res[i], x, C, Re, MaskRef{mha_mask, S, N + r0}, a.res[i], dc, dm, bufs[bi], s));
       dc = bufs[bi];
-      dm = RowMap{R, R, 0};
+      dm = RowMap{Re, Re, 0};
       bi ^= 1;
     }
     const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
-    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * R, RowMap{R, S, N}, dc, er.in, cx.G + er.w, cx.G + er.b, cx.st));
+    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, dc, er.in, cx.G + er.w, cx.G + er.b, cx.st));
   }
   return TPC_OK;
 }
@@ -272,11 +276,14 @@ struct ActorActs {
 
 // fuse != nullptr (rollout): the pointer head runs inside the fused decision kernel (decide.cu) together with the
 // pick, the environment step and the staging of the next step's inputs
-int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C, int S,
-                    ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr) {
+int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C, int N, int R,
+                    int r0, ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr) {
   const NetLayout& L = *cx.L;
   Arena& ar = *cx.ar;
   const int dff = L.dff, nl = L.nl;
+  const int S = N + R - r0;                 // compact tokens per state
+  TokWin win;
+  win.N = N; win.gap = r0; win.Sfull = N + R;
   a.y0 = ar.f((size_t)C * 128);
   RUN(small_dense_fwd(dec_input, L.demb.in, nullptr, C, RowMap{1, 1, 0}, cx.P + L.demb.w, cx.P + L.demb.b, L.demb.in,
                       a.y0, cx.st));
@@ -296,7 +303,7 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
     TPC_TRY(gemm_fwd(cx, d.o1, 128, cx.W + lp.s.wq2_t, 128, d.q2, 128, C, 128, 128, epi_bias(cx.P + lp.mha2.q.b)));
     TPC_TRY(gemm_fwd(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
                  epi_bias(cx.W + lp.s.bkvp)));
-    RUN(cross_attn_fwd(d.q2, d.kvw, mha_mask, C, S, d.ctx, d.pc, cx.st));
+    RUN(cross_attn_fwd(d.q2, d.kvw, mha_mask, C, S, d.ctx, d.pc, cx.st, win));
     TPC_TRY(gemm_fwd(cx, d.ctx, 128, cx.W + lp.s.wo2_t, 128, d.o2, 128, C, 128, 128,
                  epi_ln(cx, cx.P + lp.mha2.o.b, d.o1, lp.ln2, d.rstd2)));
     GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
@@ -312,20 +319,24 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
   if (fuse) {
     fuse->w1d = a.w1d; fuse->kvw = a.dec[nl - 1].kvw; fuse->V = cx.P + L.V.w; fuse->bV = cx.P + L.V.b;
     fuse->clipC = cx.m->dims.clip_C; fuse->has_clip = cx.m->dims.has_clip; fuse->ptr_mask = ptr_mask;
-    fuse->score = nullptr; fuse->logits = logits;
+    fuse->score = nullptr; fuse->logits = logits; fuse->win = win;
     RUN(decide_step(*fuse, C, cx.st));
     return TPC_OK;
   }
   RUN(pointer_fwd(a.w1d, a.dec[nl - 1].kvw, cx.P + L.V.w, cx.P + L.V.b, cx.m->dims.clip_C, cx.m->dims.has_clip, ptr_mask,
-                  C, S, a.score, logits, probs, argmax, cx.st));
+                  C, S, a.score, logits, probs, argmax, cx.st, win));
   return TPC_OK;
 }
 
 // dlogits [C,S] -> parameter gradients of the decoder; d_enc [C*S,128] receives the encoder-output gradient
-int decoder_backward(Ctx& cx, const float* dec_input, int C, int S, ActorActs& a, const float* dlogits, float* d_enc) {
+int decoder_backward(Ctx& cx, const float* dec_input, int C, int N, int R, int r0, ActorActs& a, const float* dlogits,
+                     float* d_enc) {
   const NetLayout& L = *cx.L;
   Arena& ar = *cx.ar;
   const int dff = L.dff, nl = L.nl;
+  const int S = N + R - r0;                 // compact tokens per state
+  TokWin win;
+  win.N = N; win.gap = r0; win.Sfull = N + R;
   float* dA = ar.f((size_t)C * 128);
   float* dB = ar.f((size_t)C * 128);
   float* dC = ar.f((size_t)C * 128);
@@ -337,7 +348,7 @@ int decoder_backward(Ctx& cx, const float* dec_input, int C, int S, ActorActs& a
   DecLayerActs& last = a.dec[nl - 1];
   if (!cx.dry()) TPC_CHECK_CUDA(cudaMemsetAsync(dkvw, 0, (size_t)C * S * 384 * sizeof(float), cx.st));
   RUN(pointer_bwd(dlogits, a.score, a.w1d, last.kvw, cx.P + L.V.w, cx.m->dims.clip_C, cx.m->dims.has_clip, C, S, dw1d,
-                  dkvw, cx.G + L.V.w, cx.G + L.V.b, cx.st));
+                  dkvw, cx.G + L.V.w, cx.G + L.V.b, cx.st, win));
   TPC_TRY(dense_grads(cx, last.o3, 128, dw1d, 128, C, L.W1));
   TPC_TRY(gemm(cx, dw1d, 128, cx.W + L.w1p_c, 128, dY, 128, C, 128, 128, GemmEpi()));
   bool enc_written = false;
@@ -378,17 +389,36 @@ int decoder_backward(Ctx& cx, const float* dec_input, int C, int S, ActorActs& a
   return TPC_OK;
 }
 
+// r0: rule tokens [0, r0) of every state are left out (TokWin); the caller guarantees they are masked in mha_mask AND
+// ptr_mask for all C states (rollout: rules placed at earlier steps; update: checked on the device, lead_masked_kernel)
 int actor_forward(Ctx& cx, StateRef sr, const float* dec_input, const float* ptr_mask, const float* mha_mask, int C,
-                  int N, int R, ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr) {
-  TPC_TRY(encoder_forward(cx, sr, mha_mask, C, N, R, a.enc));
-  return decoder_forward(cx, dec_input, ptr_mask, mha_mask, C, N + R, a, logits, probs, argmax, fuse);
+                  int N, int R, ActorActs& a, float* logits, float* probs, int32_t* argmax, DecideArgs* fuse = nullptr,
+                  int r0 = 0) {
+  TPC_TRY(encoder_forward(cx, sr, mha_mask, C, N, R, a.enc, r0));
+  return decoder_forward(cx, dec_input, ptr_mask, mha_mask, C, N, R, r0, a, logits, probs, argmax, fuse);
 }
 
 int actor_backward(Ctx& cx, StateRef sr, const float* dec_input, const float* mha_mask, int C, int N, int R,
-                   ActorActs& a, const float* dlogits) {
-  float* d_enc = cx.ar->f((size_t)C * (N + R) * 128);
-  TPC_TRY(decoder_backward(cx, dec_input, C, N + R, a, dlogits, d_enc));
-  return encoder_backward(cx, sr, mha_mask, C, N, R, a.enc, d_enc);
+                   ActorActs& a, const float* dlogits, int r0 = 0) {
+  float* d_enc = cx.ar->f((size_t)C * (N + R - r0) * 128);
+  TPC_TRY(decoder_backward(cx, dec_input, C, N, R, r0, a, dlogits, d_enc));
+  return encoder_backward(cx, sr, mha_mask, C, N, R, a.enc, d_enc, r0);
+}
+
+// Token dropping is exact only when a dropped token's logit is exactly -1e9, i.e. |C tanh(score)| < ulp(1e9) / 2 = 32
+bool can_drop_tokens(const tpc_model* m) { return m->dims.has_clip && fabsf(m->dims.clip_C) <= 30.f; }
+
+// lead[k] = min over the states of chunk k of the number of leading rule tokens that are hidden BOTH as attention keys
+// (mha_mask) and as pointer targets (ptr_mask): the window the actor may leave out for that chunk.
+__global__ void lead_masked_kernel(const float* __restrict__ mha, const float* __restrict__ ptr, long long n, int S, int N,
+                                   int chunk, int* __restrict__ lead) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* m = mha + i * S + N;
+  const float* p = ptr + i * S + N;
+  int k = 0;
+  while (k < S - N && m[k] != 0.f && p[k] != 0.f) ++k;
+  atomicMin(lead + (int)(i / chunk), k);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -494,18 +524,32 @@ int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_p
     if (ar.dry) break;
   }
   // ---- actor: policy loss (+ zero-gradient entropy term) and gradients (agents/agent.py:168-242, trainer.py:125-141)
+  // rule tokens hidden in every state of a chunk (placed at earlier steps) are left out of the actor's buffers: their
+  // count per chunk is measured on the device from the stored masks (one small read-back per update)
+  const int n_chunks = (int)((n + chunk - 1) / chunk);
+  std::vector<int> lead(n_chunks, 0);
+  if (do_actor && !ar.dry && can_drop_tokens(m)) {
+    int* d_lead = reinterpret_cast<int*>(dlogits);   // free until the first actor chunk writes it
+    TPC_CHECK_CUDA(cudaMemsetAsync(d_lead, 0x7f, n_chunks * sizeof(int), st));
+    lead_masked_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(buf->mha_masks, buf->ptr_masks, n, S, N, chunk, d_lead);
+    TPC_CHECK_LAUNCH();
+    TPC_CHECK_CUDA(cudaMemcpyAsync(lead.data(), d_lead, n_chunks * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TPC_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int& l : lead) l = l < 0 ? 0 : (l > R - 1 ? R - 1 : l);
+  }
   for (long long s0 = 0; do_actor && s0 < n; s0 += chunk) {
     const int C = (int)((n - s0) < chunk ? (n - s0) : chunk);
+    const int r0 = lead[(int)(s0 / chunk)];
     ar.off = mark;
     Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, actor_grads, &ar, stream);
     StateRef sr{buf->states + (size_t)s0 * S * F, F, cost ? buf->is_empties + (size_t)s0 * S : nullptr};
     const float* mha = buf->mha_masks + (size_t)s0 * S;
     const float* dec = buf->dec_inputs + (size_t)s0 * F;
     ActorActs a;
-    TPC_TRY(actor_forward(cx, sr, dec, buf->ptr_masks + (size_t)s0 * S, mha, C, N, R, a, logits, nullptr, nullptr));
+    TPC_TRY(actor_forward(cx, sr, dec, buf->ptr_masks + (size_t)s0 * S, mha, C, N, R, a, logits, nullptr, nullptr, nullptr, r0));
     RUN(actor_loss_bwd(logits, buf->actions + s0, advantages + s0, C, S, hp->entropy_coefficient, inv_total, dlogits,
                        losses, st));
-    TPC_TRY(actor_backward(cx, sr, dec, mha, C, N, R, a, dlogits));
+    TPC_TRY(actor_backward(cx, sr, dec, mha, C, N, R, a, dlogits, r0));
     if (!ar.fits()) return TPC_ERR_WORKSPACE;
     if (ar.dry) break;
   }
@@ -535,6 +579,19 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
       TPC_CHECK_CUDA(cudaMemcpyAsync(buf->mha_masks, buf->mha_mask, (size_t)B * S * 4, cudaMemcpyDeviceToDevice, st));
     TPC_TRY(env_feasible_mask(*e, buf->batch, F, dec_at(0), buf->bin_net_mask, B, S, pmask_at(0), st));
   }
+  // At step t the rules 0 .. t-1 are placed: hidden as attention keys by the env step itself and, as long as the rule
+  // columns of bin_net_mask are set (checked once here), never a pointer target -> the actor leaves them out.
+  bool drop = false;
+  if (!ar.dry && can_drop_tokens(m)) {
+    int* d_flag = reinterpret_cast<int*>(mask_tmp);
+    int h_flag = 0;
+    TPC_CHECK_CUDA(cudaMemsetAsync(d_flag, 0x7f, sizeof(int), st));
+    lead_masked_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(buf->bin_net_mask, buf->bin_net_mask, B, S, N, B, d_flag);
+    TPC_CHECK_LAUNCH();
+    TPC_CHECK_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TPC_CHECK_CUDA(cudaStreamSynchronize(st));
+    drop = h_flag >= R;
+  }
   for (int t = 0; t < T; ++t) {
     ar.off = mark;
     Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, stream);
@@ -557,7 +614,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
     ActorActs a;
     StateRef sr{buf->batch, F, buf->is_empty};
     TPC_TRY(actor_forward(cx, sr, ar.dry ? nullptr : dec_at(t), ar.dry ? nullptr : pmask_at(t), buf->mha_mask, B, N, R, a,
-                          buf->logits ? buf->logits + (size_t)t * B * S : nullptr, nullptr, nullptr, &da));
+                          buf->logits ? buf->logits + (size_t)t * B * S : nullptr, nullptr, nullptr, &da, drop ? t : 0));
     if (!ar.fits()) return TPC_ERR_WORKSPACE;
     if (ar.dry) break;
   }
