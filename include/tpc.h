@@ -47,7 +47,7 @@ typedef struct tpc_model_config {
   int num_bins, num_resources;                     /* TRAINING shape: critic Flatten width (critic/model.py:65) */
 } tpc_model_config;
 
-enum { TPC_ENV_RESOURCE_V3 = 0, TPC_ENV_KNAPSACK_V2 = 1 };
+enum { TPC_ENV_RESOURCE_V3 = 0, TPC_ENV_KNAPSACK_V2 = 1, TPC_ENV_CVRP = 2 };
 enum { TPC_REWARD_GREEDY = 0, TPC_REWARD_SINGLE_NODE_DOMINANT = 1, TPC_REWARD_GLOBAL_DOMINANT = 2,
        TPC_REWARD_REDUCED_NODE_USAGE = 3 };
 
@@ -182,6 +182,29 @@ typedef struct tpc_rollout_buffers {
 int tpc_rollout(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
                 const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources, int greedy, uint64_t seed,
                 int64_t episode_id0, int64_t epoch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * CVRP (environment/custom/vrp/env.py; BASELINE config #5). State (B, Nn + V, 3) fp32: rows [0, Nn) nodes [x, y, demand]
+ * (row 0 = depot), rows [Nn, Nn + V) vehicles [x, y, remaining capacity]; raw integers, un-normalised.
+ * The reference Agent cannot drive this class; tpc_cvrp_step / tpc_cvrp_feasible_mask are its
+ * methods as they are, and tpc_rollout with env kind TPC_ENV_CVRP is the single-pointer adapter (oracle/cvrp.py,
+ * DESIGN.md): num_bins = Nn, num_resources = V, T = Nn - 1 + V steps, step t serves node t + 1 (then the depot V
+ * times) and the pointer chooses the vehicle.
+ * ------------------------------------------------------------------------------------------------------ */
+/* CVRP.generate_batch replacement (vrp/env.py:148-206 samples one Augerat file; here: synthetic instances of the same
+ * form): depot and nodes at integer coordinates U{0..99}, demands U{1..max_demand}, V vehicles at the depot with
+ * `capacity`; masks as generate_masks (:208-232). Philox stream keyed by (seed, global episode id, epoch). */
+int tpc_cvrp_reset(tpc_handle* h, uint64_t seed, int64_t episode_id0, int64_t epoch, int B, int num_nodes,
+                   int num_vehicles, int max_demand, int capacity, float* batch, float* backpack_net_mask,
+                   float* item_net_mask, float* mha_mask, void* stream);
+/* CVRP.build_feasible_mask (vrp/env.py:270-301): items (B, 3) = the node rows being served. */
+int tpc_cvrp_feasible_mask(tpc_handle* h, const float* state, const float* items, const float* backpack_net_mask, int B,
+                           int S, float* out_mask, void* stream);
+/* CVRP.step(vehicle_ids, node_ids) (vrp/env.py:67-146) in place; visited_nodes = the env's counter BEFORE this step
+ * (the depot becomes selectable in item_net_mask once it reaches Nn - 2); reward (B). item_net_mask may be NULL. */
+int tpc_cvrp_step(tpc_handle* h, float* batch, float* backpack_net_mask, float* item_net_mask, float* mha_mask,
+                  const int32_t* vehicle_ids, const int32_t* node_ids, int B, int num_nodes, int num_vehicles,
+                  int visited_nodes, float* reward, void* stream);
 
 typedef struct tpc_a2c_hyper {
   float gamma, values_loss_coefficient, entropy_coefficient;  /* agents/agent.py:31-33 */

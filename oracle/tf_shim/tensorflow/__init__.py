@@ -289,6 +289,10 @@ class _Math:
             return torch.sqrt(_tt(x))
         return np.sqrt(x)
 
+    @staticmethod
+    def less(a, b):
+        return less(a, b)
+
 
 math = _Math()
 

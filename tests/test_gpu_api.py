@@ -152,6 +152,38 @@ def test_full_size_rollout_properties(reward):
         assert torch.equal(bufs.rewards.sum(1), (R - rejected).float())
 
 
+def test_initializers_follow_get_initializer():
+    """common/utils.py:49-64: `use_default_initializer` -> glorot_uniform, else U(+-1/sqrt(dims)) with dims = dim_model
+    (encoder / decoder / critic head) or attention_dense_units (pointer, pointer_attention.py:13); biases 0, gamma 1."""
+    from oracle import model as om
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import ResourceEnvironmentV3
+    agent_cfg, _, env_cfg, _, _, _ = get_configs("ResourceV3", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=4)
+    env = ResourceEnvironmentV3("ResourceV3", env_cfg, "cuda:0")
+    agent_cfg = json.loads(json.dumps(agent_cfg))
+    env.add_stats_to_agent_config(agent_cfg)
+    for default in (True, False):
+        agent_cfg["actor"]["use_default_initializer"] = agent_cfg["critic"]["use_default_initializer"] = default
+        agent = Agent("transformer", agent_cfg, "cuda:0", num_features=3, seed=3)
+        for net, spec in ((agent.bin_actor, om.actor_spec(om.NetCfg(num_layers=1, dff=128))),
+                          (agent.critic, om.critic_spec(om.NetCfg(num_layers=3, dff=512, tensor_size=31)))):
+            flat = net.get_flat()
+            offs, _ = om.spec_offsets(spec)
+            for name, (o, shape) in offs.items():
+                w = flat[o:o + int(np.prod(shape))]
+                if name.endswith(".kernel"):
+                    lim = np.sqrt(6.0 / (shape[0] + shape[1])) if default else 1.0 / np.sqrt(128)
+                    assert np.abs(w).max() <= lim and np.abs(w).max() > 0.8 * lim * (w.size > 64), name
+                elif name.endswith(".gamma"):
+                    assert np.all(w == 1), name
+                else:
+                    assert np.all(w == 0), name
+        agent.engine.close()
+
+
 @pytest.mark.parametrize("nodes,rules", [(5, 10), (50, 100)])
 def test_config2_corner_cells_replay_bit_exact_at_batch_1024(nodes, rules):
     """BASELINE config #2 (tester sweep 5-50 nodes x 10-100 rules, greedy, batch 1024): the two corner cells, 16

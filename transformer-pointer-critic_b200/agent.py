@@ -146,13 +146,16 @@ class Agent:
 
     # ------------------------------------------------------------------ weights
     def init_weights(self, seed: int = 0) -> None:
-        """Keras defaults: glorot_uniform kernels (or U(+-1/sqrt(dims)), common/utils.py:49-64), zero biases,
-        LayerNorm gamma 1 / beta 0."""
+        """Keras defaults: zero biases, LayerNorm gamma 1 / beta 0, kernels `glorot_uniform`
+        (use_default_initializer) or U(+-1/sqrt(dims)) with dims = dim_model for the encoder / decoder / MHA / FFN /
+        critic head and dims = attention_dense_units for the pointer's W1, W2, V (common/utils.py:49-64,
+        actor/pointer_attention.py:13)."""
         rng = np.random.default_rng(seed)
         for which, sub in ((0, "actor"), (1, "critic")):
             offs, sizes = self.engine.layout(which)
             flat = np.zeros(self.engine.n_params[which], dtype=np.float32)
             default = self.agent_config[sub].get("use_default_initializer", True)
+            n_pairs = len(offs) // 2
             # the canonical list alternates (kernel, bias) for Dense and (gamma, beta) for LayerNorm; a LayerNorm
             # pair is the only one with equal sizes (no Dense here has a single input feature)
             for i in range(0, len(offs), 2):
@@ -161,8 +164,9 @@ class Agent:
                     flat[offs[i]:offs[i] + n] = 1.0
                 else:
                     fan_out, fan_in = nb, n // nb
-                    lim = np.sqrt(6.0 / (fan_in + fan_out)) if default else 1.0 / np.sqrt(
-                        self.agent_config[sub]["dim_model"])
+                    pointer = which == 0 and i // 2 >= n_pairs - 3        # last_decoder_layer {W1, W2, V}
+                    dims = self.agent_config[sub]["attention_dense_units" if pointer else "dim_model"]
+                    lim = np.sqrt(6.0 / (fan_in + fan_out)) if default else 1.0 / np.sqrt(dims)
                     flat[offs[i]:offs[i] + n] = rng.uniform(-lim, lim, size=n).astype(np.float32)
             self.engine.set_params(which, flat)
 
@@ -320,7 +324,7 @@ class Agent:
         # the kernel uses draw index epoch * T + t (net.cu): advance the shared counter by whole rollouts of THIS
         # length so that neither a later rollout with another T nor step-wise act() calls can reuse a
         # (seed, episode, draw) triple
-        T = bufs.R
+        T = bufs.T
         epoch = -(-self._draw // T)
         self.engine.rollout(env._cfg_struct(), bufs, greedy, self.sample_seed, env.episode_id0, epoch)
         self._draw = (epoch + 1) * T

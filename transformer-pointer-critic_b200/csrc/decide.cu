@@ -36,16 +36,18 @@ __global__ void __launch_bounds__(256) decide_step_kernel(const DecideArgs a) {
   }
   __syncthreads();
   if (warp == 0) {
-    const float rw = env_step_warp(a.env, a.batch, a.bin_mask, nullptr, a.mha_mask, a.is_empty, c, pick_s, a.N + a.t,
-                                   a.N, a.R, lane);
-    if (lane == 0) a.rewards[(size_t)c * a.R + a.t] = rw;
+    const float rw = a.env.kind == TPC_ENV_CVRP
+                         ? cvrp_step_warp(a.batch, a.bin_mask, nullptr, a.mha_mask, c, pick_s, a.req, S, lane)
+                         : env_step_warp(a.env, a.batch, a.bin_mask, nullptr, a.mha_mask, a.is_empty, c, pick_s, a.req,
+                                         a.N, a.R, lane);
+    if (lane == 0) a.rewards[(size_t)c * a.T + a.t] = rw;
   }
-  if (a.t + 1 >= a.R) return;
+  if (a.t + 1 >= a.T) return;
   __syncthreads();   // the step's global writes are visible to the whole CTA
 
   // inputs of step t + 1, stored the way Agent.store keeps them
   const float* st = a.batch + (size_t)c * S * F;
-  const float* dec = st + (size_t)(a.N + a.t + 1) * F;
+  const float* dec = st + (size_t)a.req_next * F;
   if (threadIdx.x < F) a.dec_next[(size_t)c * F + threadIdx.x] = dec[threadIdx.x];
   if (a.states_next)
     for (int i = threadIdx.x; i < S * F; i += 256) a.states_next[(size_t)c * S * F + i] = st[i];
@@ -53,7 +55,8 @@ __global__ void __launch_bounds__(256) decide_step_kernel(const DecideArgs a) {
     const size_t o = (size_t)c * S + j;
     if (a.mha_next) a.mha_next[o] = a.mha_mask[o];
     if (a.is_empties_next) a.is_empties_next[o] = a.is_empty[o];
-    a.pmask_next[o] = feasible_elem(a.env, st + (size_t)j * F, dec, a.bin_mask[o], j);
+    a.pmask_next[o] = a.env.kind == TPC_ENV_CVRP ? cvrp_feasible_elem(st + (size_t)j * F, dec[2], a.bin_mask[o])
+                                                 : feasible_elem(a.env, st + (size_t)j * F, dec, a.bin_mask[o], j);
   }
 }
 

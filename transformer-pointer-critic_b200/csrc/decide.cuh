@@ -21,8 +21,10 @@ struct DecideArgs {
   // environment (live state, in place)
   tpc_env_config env;
   float *batch, *bin_mask, *mha_mask, *is_empty;
-  int N, R, t;             // nodes incl. EOS, rules (= steps), this step
-  float* rewards;          // (C, R)
+  int N, R, t;             // first-segment tokens (nodes incl. EOS), second-segment tokens, this step
+  int T;                   // steps of an episode (ResourceV3 / KnapsackV2: R; CVRP adapter: N - 1 + R)
+  int req, req_next;       // token index of the request served at this step / at the next one (the decoder input)
+  float* rewards;          // (C, T)
   // inputs of step t + 1 (written unless t + 1 == R); the three *_next trajectory slots may be NULL
   float *dec_next, *pmask_next, *states_next, *mha_next, *is_empties_next;
 };

@@ -116,6 +116,54 @@ __global__ void sample_kernel(const float* __restrict__ probs, int B, int S, uin
   out[b] = sample_pick(probs + (size_t)b * S, S, seed, id0 + b, draw);
 }
 
+__global__ void cvrp_reset_kernel(uint64_t seed, int64_t id0, int64_t epoch, int B, int Nn, int V, int max_demand,
+                                  int capacity, float* __restrict__ batch, float* __restrict__ backpack,
+                                  float* __restrict__ item, float* __restrict__ mha) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int S = Nn + V;
+  Stream sr = make_stream(seed, id0 + b, epoch, 5);
+  float* st = batch + (size_t)b * S * 3;
+  for (int i = 0; i < Nn; ++i) {
+    st[i * 3 + 0] = (float)sr.randint(i * 3, 0, 100);
+    st[i * 3 + 1] = (float)sr.randint(i * 3 + 1, 0, 100);
+    st[i * 3 + 2] = i == 0 ? 0.f : (float)sr.randint(i * 3 + 2, 1, max_demand + 1);
+  }
+  for (int i = Nn; i < S; ++i) {
+    st[i * 3 + 0] = st[0];
+    st[i * 3 + 1] = st[1];
+    st[i * 3 + 2] = (float)capacity;
+  }
+  for (int j = 0; j < S; ++j) {
+    backpack[(size_t)b * S + j] = j < Nn ? 1.f : 0.f;
+    if (item) item[(size_t)b * S + j] = (j >= Nn || j == 0) ? 1.f : 0.f;
+    mha[(size_t)b * S + j] = 0.f;
+  }
+}
+
+__global__ void cvrp_feasible_kernel(const float* __restrict__ state, const float* __restrict__ items,
+                                     const float* __restrict__ backpack, int B, int S, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S) return;
+  const int b = idx / S;
+  out[idx] = cvrp_feasible_elem(state + (size_t)idx * 3, items[(size_t)b * 3 + 2], backpack[idx]);
+}
+
+__global__ void cvrp_step_kernel(float* __restrict__ batch, float* __restrict__ backpack, float* __restrict__ item,
+                                 float* __restrict__ mha, const int32_t* __restrict__ vids,
+                                 const int32_t* __restrict__ nids, int B, int Nn, int V, int visited,
+                                 float* __restrict__ reward) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int S = Nn + V;
+  const float rw = cvrp_step_warp(batch, backpack, item, mha, b, vids[b], nids[b], S, lane);
+  if (lane == 0) {
+    reward[b] = rw;
+    if (item && visited + 1 == Nn - 1) item[(size_t)b * S] = 0.f;   // every node visited: the depot opens (:132-134)
+  }
+}
+
 }  // namespace
 
 int env_generate_profiles(const tpc_env_config& e, uint64_t seed, float* profiles, cudaStream_t st) {
@@ -137,7 +185,12 @@ int env_reset(const tpc_env_config& e, uint64_t seed, int64_t id0, int64_t epoch
 
 int env_feasible_mask(const tpc_env_config& e, const float* state, int ld, const float* dec, const float* bin_mask,
                       int B, int S, float* out, cudaStream_t st) {
-  feasible_mask_kernel<<<ceil_div(B * S, 256), 256, 0, st>>>(e, state, ld, dec, bin_mask, B, S, out);
+  if (e.kind == TPC_ENV_CVRP) {
+    if (ld != 3) return TPC_ERR_SHAPE;
+    cvrp_feasible_kernel<<<ceil_div(B * S, 256), 256, 0, st>>>(state, dec, bin_mask, B, S, out);
+  } else {
+    feasible_mask_kernel<<<ceil_div(B * S, 256), 256, 0, st>>>(e, state, ld, dec, bin_mask, B, S, out);
+  }
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
@@ -163,6 +216,43 @@ int sample_categorical(const float* probs, int B, int S, uint64_t seed, int64_t 
 using namespace tpc;
 
 extern "C" {
+
+int tpc_cvrp_reset(tpc_handle* h, uint64_t seed, int64_t episode_id0, int64_t epoch, int B, int num_nodes,
+                   int num_vehicles, int max_demand, int capacity, float* batch, float* backpack_net_mask,
+                   float* item_net_mask, float* mha_mask, void* stream) {
+  if (!h || !batch || !backpack_net_mask || !mha_mask) return TPC_ERR_ARG;
+  if (B < 0 || num_nodes < 2 || num_vehicles < 1 || max_demand < 1 || capacity < max_demand) return TPC_ERR_SHAPE;
+  if (B == 0) return TPC_OK;
+  cvrp_reset_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(seed, episode_id0, epoch, B, num_nodes, num_vehicles,
+                                                                    max_demand, capacity, batch, backpack_net_mask,
+                                                                    item_net_mask, mha_mask);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_cvrp_feasible_mask(tpc_handle* h, const float* state, const float* items, const float* backpack_net_mask, int B,
+                           int S, float* out_mask, void* stream) {
+  if (!h || !state || !items || !backpack_net_mask || !out_mask) return TPC_ERR_ARG;
+  if (B < 0 || S < 1) return TPC_ERR_SHAPE;
+  if (B == 0) return TPC_OK;
+  cvrp_feasible_kernel<<<ceil_div(B * S, 256), 256, 0, (cudaStream_t)stream>>>(state, items, backpack_net_mask, B, S,
+                                                                             out_mask);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int tpc_cvrp_step(tpc_handle* h, float* batch, float* backpack_net_mask, float* item_net_mask, float* mha_mask,
+                  const int32_t* vehicle_ids, const int32_t* node_ids, int B, int num_nodes, int num_vehicles,
+                  int visited_nodes, float* reward, void* stream) {
+  if (!h || !batch || !backpack_net_mask || !mha_mask || !vehicle_ids || !node_ids || !reward) return TPC_ERR_ARG;
+  if (B < 0 || num_nodes < 2 || num_vehicles < 1) return TPC_ERR_SHAPE;
+  if (B == 0) return TPC_OK;
+  cvrp_step_kernel<<<ceil_div(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(batch, backpack_net_mask, item_net_mask, mha_mask,
+                                                                          vehicle_ids, node_ids, B, num_nodes,
+                                                                          num_vehicles, visited_nodes, reward);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
 
 int tpc_env_generate_profiles(tpc_handle* h, const tpc_env_config* e, uint64_t seed, float* profiles, void* stream) {
   if (!h || !e || !profiles) return TPC_ERR_ARG;

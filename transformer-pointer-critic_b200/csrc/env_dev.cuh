@@ -101,6 +101,45 @@ __device__ __forceinline__ float env_step_warp(const tpc_env_config& e, float* _
   return rw;
 }
 
+// ---- CVRP (environment/custom/vrp/env.py) ------------------------------------------------------------------------
+// build_feasible_mask for position j (:270-301): w = demand of the served node
+__device__ __forceinline__ float cvrp_feasible_elem(const float* __restrict__ row, float w, float backpack_mask_j) {
+  const float tot = __fmul_rn(__fsub_rn(row[2], w), __fsub_rn(1.f, backpack_mask_j));
+  return fmaxf(tot < 0.f ? 1.f : 0.f, backpack_mask_j);
+}
+// step(vehicle, node) of episode b by one warp (:67-146): returns the reward -round(distance) on every lane.
+// item_mask may be nullptr (the single-pointer rollout serves the nodes in sequence order and never reads it).
+__device__ __forceinline__ float cvrp_step_warp(float* __restrict__ batch, float* __restrict__ backpack_mask,
+                                                float* __restrict__ item_mask, float* __restrict__ mha_mask, int b,
+                                                int veh, int node, int S, int lane) {
+  veh = min(max(veh, 0), S - 1);
+  node = min(max(node, 0), S - 1);
+  float* st = batch + (size_t)b * S * 3;
+  const float nx = st[node * 3], ny = st[node * 3 + 1], nd = st[node * 3 + 2];
+  const float vx = st[veh * 3], vy = st[veh * 3 + 1], vc = st[veh * 3 + 2];
+  const float xd = __fsub_rn(vx, nx), yd = __fsub_rn(vy, ny);
+  // round(sqrt(xd*xd + yd*yd)): float32 products and sum, float64 sqrt, Python round (half to even)
+  const float d2 = __fadd_rn(__fmul_rn(xd, xd), __fmul_rn(yd, yd));
+  const float rw = -(float)rint(sqrt((double)d2));
+  __syncwarp();
+  if (lane == 0) {
+    st[veh * 3] = nx;
+    st[veh * 3 + 1] = ny;
+    st[veh * 3 + 2] = __fsub_rn(vc, nd);
+    if (nd != 0.f) {
+      if (item_mask) item_mask[(size_t)b * S + node] = 1.f;
+      mha_mask[(size_t)b * S + node] = 1.f;
+    } else {
+      backpack_mask[(size_t)b * S + veh] = 1.f;
+      mha_mask[(size_t)b * S + veh] = 1.f;
+    }
+  }
+  __syncwarp();
+  return rw;
+}
+// adapter: token index of the node served at step t
+__host__ __device__ inline int cvrp_request(int t, int num_nodes) { return t < num_nodes - 1 ? t + 1 : 0; }
+
 // tfp Categorical(probs).sample() substitute: inverse-CDF draw on the Philox uniform (seed, episode id, draw index);
 // a sequential fp32 running sum over p[0..S) (p may live in shared or global memory)
 __device__ __forceinline__ int sample_pick(const float* p, int S, uint64_t seed, int64_t id, int64_t draw) {

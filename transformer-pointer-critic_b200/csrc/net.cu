@@ -560,7 +560,10 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
                  const tpc_rollout_buffers* buf, int B, int N, int R, int greedy, uint64_t seed, int64_t id0,
                  int64_t epoch, Arena& ar, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int S = N + R, T = R, F = e->num_features;
+  const bool cvrp = e->kind == TPC_ENV_CVRP;
+  const int S = N + R, F = e->num_features;
+  const int T = cvrp ? N - 1 + R : R;                     // CVRP adapter: N - 1 node visits + R returns to the depot
+  auto req_at = [&](int t) { return cvrp ? (t < N - 1 ? t + 1 : 0) : N + t; };   // CVRP: oracle/cvrp.py request_node
   float* dec_tmp = ar.f((size_t)B * F);
   float* mask_tmp = ar.f((size_t)B * S);
   const size_t mark = ar.off;
@@ -569,7 +572,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
   if (!ar.dry) {
     // inputs of step 0: decoder input = first rule, Agent.store copies (agents/trainer.py:68-76), feasible mask.
     // For every later step the fused decision kernel of step t - 1 stages them.
-    gather_dec_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(buf->batch, B, S, F, N, dec_at(0));
+    gather_dec_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(buf->batch, B, S, F, req_at(0), dec_at(0));
     TPC_CHECK_LAUNCH();
     if (buf->states)
       TPC_CHECK_CUDA(cudaMemcpyAsync(buf->states, buf->batch, (size_t)B * S * F * 4, cudaMemcpyDeviceToDevice, st));
@@ -582,7 +585,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
   // At step t the rules 0 .. t-1 are placed: hidden as attention keys by the env step itself and, as long as the rule
   // columns of bin_net_mask are set (checked once here), never a pointer target -> the actor leaves them out.
   bool drop = false;
-  if (!ar.dry && can_drop_tokens(m)) {
+  if (!ar.dry && !cvrp && can_drop_tokens(m)) {
     int* d_flag = reinterpret_cast<int*>(mask_tmp);
     int h_flag = 0;
     TPC_CHECK_CUDA(cudaMemsetAsync(d_flag, 0x7f, sizeof(int), st));
@@ -601,7 +604,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
       da.actions = buf->actions + (size_t)t * B;
       da.env = *e;
       da.batch = buf->batch; da.bin_mask = buf->bin_net_mask; da.mha_mask = buf->mha_mask; da.is_empty = buf->is_empty;
-      da.N = N; da.R = R; da.t = t;
+      da.N = N; da.R = R; da.t = t; da.T = T; da.req = req_at(t); da.req_next = req_at(t + 1 < T ? t + 1 : t);
       da.rewards = buf->rewards;
       if (t + 1 < T) {
         da.dec_next = dec_at(t + 1);

@@ -213,9 +213,11 @@ class RolloutTensors:
     """Device buffers of one rollout: the live env state + the trajectory memory (Agent.store, agent.py:75-95)."""
 
     def __init__(self, B: int, N: int, R: int, F: int, device, cost: bool = False, store: bool = True,
-                 keep_logits: bool = False):
+                 keep_logits: bool = False, T: int | None = None):
         self.B, self.N, self.R, self.F = B, N, R, F
-        S, T = N + R, R
+        S = N + R
+        T = R if T is None else T      # steps per episode (CVRP adapter: N - 1 + R)
+        self.T = T
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         self.batch, self.bin_net_mask, self.mha_mask = f(B, S, F), f(B, S), f(B, S)
         self.is_empty = f(B, S) if cost else None

@@ -280,8 +280,159 @@ class KnapsackEnvironmentV2(_DeviceEnvBase):
 def env_factory(type: str, name: str, opts: dict, device="cuda:0"):
     """environment/env_factory.py:27-33 -> (env, tester)."""
     from .tester import knapsack_test, test as resource_tester
-    table = {"ResourceV3": (ResourceEnvironmentV3, resource_tester), "KnapsackV2": (KnapsackEnvironmentV2, knapsack_test)}
+    table = {"ResourceV3": (ResourceEnvironmentV3, resource_tester), "KnapsackV2": (KnapsackEnvironmentV2, knapsack_test),
+             "CVRP": (CVRP, None)}                      # environment/env_factory.py:22: CVRP has no tester
     if type != "custom" or name not in table:
         raise NameError(f"Unknown environment {type}/{name}")
     env_cls, tester = table[name]
     return env_cls(name, opts, device), tester
+
+
+class CVRP:
+    """environment/custom/vrp/env.py:14-301 on the device, with the reference's own (double-index) interface --
+    `reset() -> (batch, backpack_net_mask, item_net_mask, mha_used_mask)`, `step(vehicle_ids, node_ids) -> (batch,
+    rewards, isDone, info)`, `build_feasible_mask(state, items, backpack_net_mask)` -- and the single-pointer adapter the
+    fused rollout uses (`device_buffers` / `reset_into` / `Agent.rollout`): step t serves node t + 1 (then the depot once
+    per vehicle) and the pointer chooses the vehicle; every adapter step is one reference `step(vehicle, node)`.
+
+    The reference samples its batch from one Augerat instance file (`dir_path` / `problem_name`, :27-45); instance files
+    are out of scope here, so `reset` draws synthetic instances of the same form (integer coordinates 0..99, demands
+    1..`max_demand`, `vehicle_capacity`), and `load_batch` installs a given batch (e.g. one parsed elsewhere)."""
+    KIND = 2
+
+    def __init__(self, name: str, opts: dict, device="cuda:0"):
+        self.name, self.opts = name, opts
+        self.device = torch.device(device)
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        L.check(self.lib.tpc_create(C.byref(self.h)), "tpc_create")
+        self.batch_size = opts["batch_size"]
+        self.node_sample_size = opts["node_sample_size"]          # incl. the depot (row 0)
+        self.vehicle_sample_size = opts["vehicle_sample_size"]
+        self.num_features = opts["num_features"]
+        if self.num_features != 3:
+            raise ValueError("CVRP rows are [x, y, demand | capacity]: num_features must be 3")
+        self.max_demand = int(opts.get("max_demand", 24))
+        self.vehicle_capacity = int(opts.get("vehicle_capacity", 100))
+        self.seed_value = int(opts.get("seed_value", 1235))
+        self.episode_id0, self.epoch, self.visited_nodes = 0, 0, 0
+        cfg = L.EnvConfig()
+        cfg.kind, cfg.num_features = self.KIND, 3
+        self._cfg = cfg
+        self.reset()
+
+    # the names Agent.rollout / trainer-side code use for the two token segments
+    @property
+    def profiles_sample_size(self):
+        return self.vehicle_sample_size
+
+    @property
+    def tensor_size(self):
+        return self.node_sample_size + self.vehicle_sample_size
+
+    @property
+    def steps(self):
+        return self.node_sample_size - 1 + self.vehicle_sample_size
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _cfg_struct(self):
+        return self._cfg
+
+    def _alloc(self):
+        B, S = self.batch_size, self.tensor_size
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.batch_d, self.backpack_net_mask_d, self.item_net_mask_d, self.mha_mask_d = f(B, S, 3), f(B, S), f(B, S), f(B, S)
+
+    def reset(self):
+        """:50-65."""
+        self.visited_nodes = 0
+        self._alloc()
+        L.check(self.lib.tpc_cvrp_reset(self.h, self.seed_value, self.episode_id0, self.epoch, self.batch_size,
+                                        self.node_sample_size, self.vehicle_sample_size, self.max_demand,
+                                        self.vehicle_capacity, L.ptr(self.batch_d), L.ptr(self.backpack_net_mask_d),
+                                        L.ptr(self.item_net_mask_d), L.ptr(self.mha_mask_d), self.stream), "tpc_cvrp_reset")
+        self.epoch += 1
+        return self.state()
+
+    def load_batch(self, batch):
+        batch = torch.as_tensor(np.asarray(batch, dtype=np.float32))
+        self.batch_size, self.visited_nodes = batch.shape[0], 0
+        self._alloc()
+        Nn = self.node_sample_size
+        self.batch_d.copy_(batch.to(self.device))
+        self.backpack_net_mask_d[:, :Nn] = 1
+        self.item_net_mask_d[:, Nn:] = 1
+        self.item_net_mask_d[:, 0] = 1
+        return self.state()
+
+    def state(self):
+        """:61-65."""
+        return (_host(self.batch_d), _host(self.backpack_net_mask_d), _host(self.item_net_mask_d),
+                _host(self.mha_mask_d)[:, None, None, :])
+
+    def request_node(self, t: int) -> int:
+        return t + 1 if t < self.node_sample_size - 1 else 0
+
+    def build_feasible_mask(self, state, items, backpack_net_mask):
+        """:270-301."""
+        st = torch.as_tensor(np.ascontiguousarray(state, dtype=np.float32)).to(self.device)
+        it = torch.as_tensor(np.ascontiguousarray(items, dtype=np.float32)).to(self.device).reshape(st.shape[0], -1)
+        bm = torch.as_tensor(np.ascontiguousarray(backpack_net_mask, dtype=np.float32)).to(self.device)
+        out = torch.empty_like(bm)
+        L.check(self.lib.tpc_cvrp_feasible_mask(self.h, L.ptr(st), L.ptr(it), L.ptr(bm), st.shape[0], st.shape[1],
+                                                L.ptr(out), self.stream), "tpc_cvrp_feasible_mask")
+        return _host(out)
+
+    def step(self, vehicle_ids, node_ids):
+        """:67-146."""
+        B, S = self.batch_size, self.tensor_size
+        ids = []
+        for a in (vehicle_ids, node_ids):
+            a = np.asarray(a, dtype=np.int32).reshape(-1)
+            if a.shape[0] != B:
+                raise ValueError(f"step() expects one id per episode ({B})")
+            if a.size and (a.min() < -S or a.max() >= S):
+                raise IndexError(f"index out of bounds for axis 1 with size {S}")
+            ids.append(torch.as_tensor(np.where(a < 0, a + S, a).astype(np.int32)).to(self.device))
+        state, _, _, _ = self.state()
+        v, n = ids[0].cpu().numpy(), ids[1].cpu().numpy()
+        if np.any(state[np.arange(B), v, 2] - state[np.arange(B), n, 2] < 0):   # the reference's assert (:97-98)
+            raise AssertionError("Vehicle is overloaded")
+        reward = torch.empty(B, dtype=torch.float32, device=self.device)
+        L.check(self.lib.tpc_cvrp_step(self.h, L.ptr(self.batch_d), L.ptr(self.backpack_net_mask_d),
+                                       L.ptr(self.item_net_mask_d), L.ptr(self.mha_mask_d), L.ptr(ids[0]), L.ptr(ids[1]),
+                                       B, self.node_sample_size, self.vehicle_sample_size, self.visited_nodes,
+                                       L.ptr(reward), self.stream), "tpc_cvrp_step")
+        self.visited_nodes += 1
+        is_done = self.visited_nodes == self.steps
+        batch, bp, item, mha = self.state()
+        info = {"backpack_net_mask": bp, "item_net_mask": item, "mha_used_mask": mha,
+                "num_items_to_place": self.node_sample_size}
+        return batch, _host(reward).reshape(B, 1).view(HostTensor), is_done, info
+
+    def add_stats_to_agent_config(self, agent_config: dict):
+        """:234-247 (`num_items`, `tensor_size`, `num_backpacks`, `batch_size`) plus the keys the single-pointer Agent
+        reads (agents/agent.py:25-29, resource_v3/env.py:314-334): nodes are the first token segment, vehicles the second."""
+        agent_config["num_items"] = self.steps
+        agent_config["tensor_size"] = self.tensor_size
+        agent_config["num_backpacks"] = self.vehicle_sample_size
+        agent_config["batch_size"] = self.batch_size
+        agent_config["num_bins"] = self.node_sample_size
+        agent_config["num_resources"] = self.vehicle_sample_size
+        agent_config["encoder_embedding"] = {"common": True, "num_bin_features": None, "num_resource_features": None}
+        return agent_config
+
+    # -- fused path (single-pointer adapter) ---------------------------------------------------------------
+    def device_buffers(self, store=True, keep_logits=False) -> RolloutTensors:
+        return RolloutTensors(self.batch_size, self.node_sample_size, self.vehicle_sample_size, 3, self.device,
+                              store=store, keep_logits=keep_logits, T=self.steps)
+
+    def reset_into(self, bufs: RolloutTensors) -> None:
+        L.check(self.lib.tpc_cvrp_reset(self.h, self.seed_value, self.episode_id0, self.epoch, bufs.B, bufs.N, bufs.R,
+                                        self.max_demand, self.vehicle_capacity, L.ptr(bufs.batch),
+                                        L.ptr(bufs.bin_net_mask), None, L.ptr(bufs.mha_mask), self.stream),
+                "tpc_cvrp_reset")
+        self.epoch += 1

@@ -78,6 +78,11 @@ SIGNATURES = {
                                       c_int, c_void_p, c_void_p]),
     "tpc_env_step": (c_int, [c_void_p, C.POINTER(EnvConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tpc_cvrp_reset": (c_int, [c_void_p, c_u64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    "tpc_cvrp_feasible_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tpc_cvrp_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_int, c_void_p, c_void_p]),
     "tpc_sample_categorical": (c_int, [c_void_p, c_void_p, c_int, c_int, c_u64, c_i64, c_i64, c_void_p, c_void_p]),
     "tpc_rollout": (c_int, [c_void_p, C.POINTER(EnvConfig), c_void_p, c_void_p, C.POINTER(RolloutBuffers), c_int,
                             c_int, c_int, c_int, c_u64, c_i64, c_i64, c_void_p, c_size_t, c_void_p]),
