@@ -84,6 +84,10 @@ size_t tpc_param_count(const tpc_model* m, int which);
 int tpc_num_tensors(const tpc_model* m, int which);
 /* HOST out arrays of length tpc_num_tensors: offset and size of each canonical tensor */
 int tpc_param_layout(const tpc_model* m, int which, int64_t* offsets, int64_t* sizes);
+/* Name and shape of canonical tensor `index` (Keras `trainable_weights` order, e.g. "encoder.enc_layers.0.mha.wq.kernel"):
+ * kernels are [rows][cols] = [in][out], 1-D tensors report cols = 0. Used by the weight interchange
+ * (agents/agent.py:289-294: Keras attribute paths of a TF checkpoint). */
+int tpc_param_info(const tpc_model* m, int which, int index, char* name, int name_capacity, int64_t* rows, int64_t* cols);
 /* floats in the kernel-side weight image (transposed / fused / TF32-rounded copies) */
 size_t tpc_shadow_count(const tpc_model* m, int which);
 /* rebuild the weight image after params changed (after load_weights / every optimizer step) */

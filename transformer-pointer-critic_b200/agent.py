@@ -59,13 +59,50 @@ class _Net:
     def set_flat(self, flat) -> None:
         self.engine.set_params(self.which, flat)
 
+    def _named_tensors(self) -> dict:
+        """{Keras attribute path: ndarray} in `trainable_weights` order (tf_checkpoint.keras_path)."""
+        from . import tf_checkpoint as tfc
+        names = self.engine.tensor_names(self.which)
+        offs, sizes = self.engine.layout(self.which)
+        shapes = self.engine.tensor_shapes(self.which)
+        flat = self.get_flat()
+        return {tfc.keras_path(n): flat[o:o + k].reshape(s) for n, o, k, s in zip(names, offs, sizes, shapes)}
+
     def save_weights(self, location: str) -> None:
+        """keras.Model.save_weights(location) (agents/agent.py:289-290). A path without `.npz` gets what Keras writes
+        for it -- a TF checkpoint `<location>.index` + `<location>.data-00000-of-00001` (tf_checkpoint.py; the format
+        could not be verified against TensorFlow itself) -- and a flat `<location>.npz` beside it; `*.npz` gets the
+        flat file only."""
         os.makedirs(os.path.dirname(os.path.abspath(location)) or ".", exist_ok=True)
         offs, sizes = self.engine.layout(self.which)
         np.savez(location if location.endswith(".npz") else location + ".npz", flat=self.get_flat(),
-                 offsets=np.asarray(offs), sizes=np.asarray(sizes))
+                 offsets=np.asarray(offs), sizes=np.asarray(sizes), names=np.asarray(self.engine.tensor_names(self.which)))
+        if not location.endswith(".npz"):
+            from . import tf_checkpoint as tfc
+            tfc.write_checkpoint(location, self._named_tensors())
+            base = os.path.basename(location)
+            with open(os.path.join(os.path.dirname(os.path.abspath(location)), "checkpoint"), "w") as f:
+                f.write(f'model_checkpoint_path: "{base}"\nall_model_checkpoint_paths: "{base}"\n')
 
     def load_weights(self, location: str) -> None:
+        """keras.Model.load_weights(location) (agents/agent.py:293-294): a TF checkpoint written by the reference (or
+        by save_weights above) when `<location>.index` exists, else the flat `.npz`."""
+        if not location.endswith(".npz") and os.path.exists(location + ".index"):
+            from . import tf_checkpoint as tfc
+            stored = tfc.read_checkpoint(location)
+            names = self.engine.tensor_names(self.which)
+            offs, sizes = self.engine.layout(self.which)
+            shapes = self.engine.tensor_shapes(self.which)
+            flat = np.zeros(self.engine.n_params[self.which], dtype=np.float32)
+            for n, o, k, s in zip(names, offs, sizes, shapes):
+                key = tfc.keras_path(n)
+                if key not in stored:
+                    raise ValueError(f"{location}: variable {key} is missing from the checkpoint")
+                if tuple(stored[key].shape) != tuple(s):
+                    raise ValueError(f"{location}: {key} has shape {stored[key].shape}, this network expects {tuple(s)}")
+                flat[o:o + k] = stored[key].reshape(-1)
+            self.set_flat(flat)
+            return
         path = location if location.endswith(".npz") else location + ".npz"
         with np.load(path) as z:
             offs, sizes = self.engine.layout(self.which)

@@ -15,7 +15,7 @@ struct Builder {
   DenseP dense(const std::string& name, int in, int out) {
     DenseP p;
     p.in = in; p.out = out;
-    p.w = off; L->tensors.push_back({off, (size_t)in * out, name + ".kernel"}); off += (size_t)in * out;
+    p.w = off; L->tensors.push_back({off, (size_t)in * out, name + ".kernel", in}); off += (size_t)in * out;
     p.b = off; L->tensors.push_back({off, (size_t)out, name + ".bias"}); off += out;
     return p;
   }
@@ -289,6 +289,18 @@ int tpc_param_layout(const tpc_model* m, int which, int64_t* offsets, int64_t* s
     offsets[i] = (int64_t)L.tensors[i].off;
     sizes[i] = (int64_t)L.tensors[i].n;
   }
+  return TPC_OK;
+}
+
+int tpc_param_info(const tpc_model* m, int which, int index, char* name, int name_capacity, int64_t* rows,
+                   int64_t* cols) {
+  if (!m || !name || name_capacity < 1 || !rows || !cols) return TPC_ERR_ARG;
+  const NetLayout& L = which ? m->critic : m->actor;
+  if (index < 0 || index >= (int)L.tensors.size()) return TPC_ERR_SHAPE;
+  const TensorInfo& t = L.tensors[index];
+  snprintf(name, (size_t)name_capacity, "%s", t.name.c_str());
+  *rows = t.rows > 0 ? t.rows : (int64_t)t.n;
+  *cols = t.rows > 0 ? (int64_t)(t.n / t.rows) : 0;
   return TPC_OK;
 }
 

@@ -41,7 +41,7 @@ struct EncoderP {
   bool common = true;
   std::vector<EncLayerP> joint, bins, res;  // enc_layers, enc_layers_bins, enc_layers_resources
 };
-struct TensorInfo { size_t off, n; std::string name; };
+struct TensorInfo { size_t off, n; std::string name; int rows = 0; };   // rows > 0: kernel [rows][n / rows]
 
 struct NetLayout {
   bool is_actor = true;

@@ -125,6 +125,21 @@ class Engine:
         L.check(self.lib.tpc_param_layout(self.m, which, offs, sizes), "tpc_param_layout")
         return list(offs), list(sizes)
 
+    def _tensor_info(self, which: int):
+        out = []
+        buf = C.create_string_buffer(256)
+        rows, cols = C.c_int64(), C.c_int64()
+        for i in range(self.lib.tpc_num_tensors(self.m, which)):
+            L.check(self.lib.tpc_param_info(self.m, which, i, buf, 256, C.byref(rows), C.byref(cols)), "tpc_param_info")
+            out.append((buf.value.decode(), (rows.value, cols.value) if cols.value else (rows.value,)))
+        return out
+
+    def tensor_names(self, which: int):
+        return [n for n, _ in self._tensor_info(which)]
+
+    def tensor_shapes(self, which: int):
+        return [s for _, s in self._tensor_info(which)]
+
     def set_params(self, which: int, flat) -> None:
         t = torch.as_tensor(np.asarray(flat, dtype=np.float32)) if not torch.is_tensor(flat) else flat
         if t.numel() != self.n_params[which]:

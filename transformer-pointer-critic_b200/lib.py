@@ -56,6 +56,7 @@ SIGNATURES = {
     "tpc_param_count": (c_size_t, [c_void_p, c_int]),
     "tpc_num_tensors": (c_int, [c_void_p, c_int]),
     "tpc_param_layout": (c_int, [c_void_p, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "tpc_param_info": (c_int, [c_void_p, c_int, c_int, C.c_char_p, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "tpc_shadow_count": (c_size_t, [c_void_p, c_int]),
     "tpc_prepare_weights": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tpc_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
