@@ -62,7 +62,9 @@ def test_fused_cvrp_rollout_replays_through_the_oracle(Nn, V, B, greedy):
     from tpc_b200.configs import get_configs
     agent_cfg, _, env_cfg, _, _, _ = get_configs("CVRP", "tpc")
     env_cfg = json.loads(json.dumps(env_cfg))
-    env_cfg.update(batch_size=B, node_sample_size=Nn, vehicle_sample_size=V)
+    # capacity 200: V * (200 - 24) exceeds the largest possible total demand, so no sampled trajectory can reach a node
+    # that fits no vehicle (the reference asserts there, vrp/env.py:97-98; a dead end has no defined continuation)
+    env_cfg.update(batch_size=B, node_sample_size=Nn, vehicle_sample_size=V, vehicle_capacity=200)
     from tpc_b200.env import env_factory
     env, tester = env_factory("custom", "CVRP", env_cfg)
     assert tester is None
