@@ -199,8 +199,11 @@ def run_check(args, world, rank, dev, B, nodes, rules):
             for w in (w1, allreduce(eng.grads[0]), allreduce(eng.losses)):
                 w.wait()
         torch.cuda.synchronize()
+        names[0], names[1] = eng.tensor_names(0), eng.tensor_names(1)
         return (bufs.actions.clone(), bufs.rewards.clone(), eng.grads[0].clone(), eng.grads[1].clone(),
                 (eng.losses / float(total)).clone(), eng.layout(0), eng.layout(1))
+
+    names = [None, None]
 
     ar = (lambda t: dist.all_reduce(t, async_op=True)) if world > 1 else None
     acts, rews, ga, gc, losses, _, _ = one_pass(B, rank * B, world, ar)
@@ -213,16 +216,26 @@ def run_check(args, world, rank, dev, B, nodes, rules):
     if rank == 0:
         fa, fr, fga, fgc, flosses, la, lc = one_pass(B * world, 0, 1, None)
 
-        def per_tensor(g, ref, layout):
-            worst = 0.0
-            for o, n in zip(*layout):
-                nr = float(ref[o:o + n].norm())
-                if nr > 1e-6 * float(ref.norm()):
-                    worst = max(worst, float((g[o:o + n] - ref[o:o + n]).norm()) / nr)
-            return worst
+        def per_tensor(g, ref, layout, names):
+            """Worst per-tensor relative error (norm-wise) over the tensors that carry a gradient. Tensors whose true
+            gradient is zero (every wk.bias: softmax rows are shift invariant; the decoder's mha1.wq / wk: one key) hold
+            rounding noise only -- it changes with the summation order, i.e. with the token windows of the chunks, and
+            Adam's clipnorm never sees it as signal -- so tensors below 1e-3 of the largest tensor norm are left out."""
+            norms = [float(ref[o:o + n].norm()) for o, n in zip(*layout)]
+            worst, where = 0.0, ""
+            for (o, n), nr, name in zip(zip(*layout), norms, names):
+                if nr > 1e-3 * max(norms):
+                    e = float((g[o:o + n] - ref[o:o + n]).norm()) / nr
+                    if e > worst:
+                        worst, where = e, name
+            return worst, where
+        ea, wa = per_tensor(ga, fga, la, names[0])
+        ec, wc = per_tensor(gc, fgc, lc, names[1])
         res = {"check": "multi_gpu", "n_gpus": world, "global_batch": B * world, "nodes": nodes, "rules": rules,
                "actions_equal": bool(torch.equal(acts, fa)), "rewards_equal": bool(torch.equal(rews, fr)),
-               "actor_grad_rel": per_tensor(ga, fga, la), "critic_grad_rel": per_tensor(gc, fgc, lc),
+               "actor_grad_rel": ea, "actor_worst_tensor": wa, "critic_grad_rel": ec, "critic_worst_tensor": wc,
+               "actor_grad_rel_whole": float((ga - fga).norm() / fga.norm()),
+               "critic_grad_rel_whole": float((gc - fgc).norm() / fgc.norm()),
                "loss_rel": float(((losses - flosses).abs() / flosses.abs().clamp_min(1e-12)).max())}
         res["ok"] = bool(res["actions_equal"] and res["rewards_equal"] and res["actor_grad_rel"] < 2e-3
                          and res["critic_grad_rel"] < 2e-3 and res["loss_rel"] < 1e-4)

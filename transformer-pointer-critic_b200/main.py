@@ -52,6 +52,12 @@ def runner(env_type="custom", env_name="ResourceV3", agent_name="tpc", device="c
     """main.py:40-83. `overrides` = {"trainer_config": {...}, "env_config": {...}, "tester_config": {...}} is applied on
     top of configs/<env_name>.json (the reference edits the JSON file instead)."""
     start_date = datetime.now().replace(microsecond=0).isoformat()
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # one log directory per job: rank 0's timestamp (every rank stamping its own would scatter config.json / env.txt)
+        stamp = [start_date]
+        dist.broadcast_object_list(stamp, src=0)
+        start_date = stamp[0]
     agent_config, trainer_config, env_config, tester_config, _, all_configs = get_configs(env_name, agent_name)
     for section, target in (("trainer_config", trainer_config), ("env_config", env_config),
                             ("tester_config", tester_config)):
