@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtpc.so")
+LIB_PATH = os.environ.get("TPC_LIB") or os.path.join(_HERE, "libtpc.so")   # TPC_LIB: A/B runs of two builds
 
 c_int, c_float, c_void_p, c_size_t = C.c_int, C.c_float, C.c_void_p, C.c_size_t
 c_u64, c_i64 = C.c_uint64, C.c_int64
