@@ -49,4 +49,4 @@ if not os.environ.get('SKIP_CHECK'):
     for (Cn, Lt, fm) in [(5, 151, 0.3), (7, 100, 0.5), (9, 51, 0.0), (3, 16, 0.25)]:
         run(Cn, Lt, fm, True)
 for (Lt, fm) in [(151, 0.0), (151, 0.33), (100, 0.5), (51, 0.1)]:
-    run(2048, Lt, fm, False)
+    run(int(os.environ.get('STATES', 2048)), Lt, fm, False)
