@@ -1,4 +1,5 @@
-"""Quick perf probe at the headline shape (B=1024, 50 nodes x 100 rules)."""
+"""Quick perf probe: rollout / update / Adam split and host launch time (default: the headline shape B=1024, 50 nodes x
+100 rules; B= N= R= select another one, e.g. B=128 N=11 R=20 for the shipped config)."""
 import ctypes as C, json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +10,7 @@ from tpc_b200.engine import Engine, RolloutTensors, env_config_struct
 from tests.gpu_checks.check_model import make_cfg
 
 dev = torch.device("cuda:0")
-B = int(os.environ.get("B", 1024)); N, R, F = 51, 100, 3
+B = int(os.environ.get("B", 1024)); N, R, F = int(os.environ.get("N", 51)), int(os.environ.get("R", 100)), 3
 chunk = int(os.environ.get("CHUNK", 10240))
 cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "env_rv3_shipped_greedy.json")))
 mc, ca, cc = make_cfg(N, R)
