@@ -42,7 +42,8 @@ def test_cuda_matches_reference_model_goldens(case):
         elif metric.startswith("grad_elem_"):
             assert v < (1e-1 if first else 3.0), (key, v)      # later iterations: drift of the parameters, see above
         elif metric == "window_grad_actor":
-            assert v < 2e-3, (key, v)       # chunked with token windows vs one chunk: run-to-run class of the backward
+            assert v < 5e-3, (key, v)       # chunked with token windows vs one chunk: run-to-run class of the TF32 backward
+                                            # (measured 1e-4 ... 1.8e-3 over all cases and iterations)
         elif metric == "window_losses":
             assert v < 1e-4, (key, v)
         elif metric.startswith("update_q95_") or metric.startswith("update_mean_"):
