@@ -58,6 +58,31 @@ int cross_attn_fwd(const float* q2, const float* kvw, const float* mask, int C, 
 int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const float* pc, int C, int S, float* dq2,
                    float* dkvw, cudaStream_t st);
 
+// One decoder layer on the single decoder token of every state (actor/decoder.py:74-81, actor/decoder_layer.py:18-32) as
+// ONE kernel, 4 states per CTA, fp32 FMA on CUDA cores (the products are [4 x 128] x [128 x 128]: GEMV-sized, a
+// 148-CTA tensor-core launch each would cost more in launch latency than in arithmetic):
+//   [y0 = Dense_emb(dec_input)]                          first layer only (y_in == nullptr)
+//   v1 = Dense_v1(y); o1 = LN1(Dense_o1(v1) + y)          mha1 over one key: softmax == 1
+//   q2 = Dense_q2(o1); ctx = softmax(q2 K2^T / 4 + mask * -1e9) V2 per head over the S compact tokens of kvw
+//   o2 = LN2(Dense_o2(ctx) + o1); f = relu(Dense_f1(o2)); o3 = LN3(Dense_f2(f) + o2)
+//   [w1d = Dense_W1(o3)]                                 last layer only (Wp1 != nullptr): pointer_attention.py:43
+// Every intermediate is also written to global memory: the backward pass reads them (agents/trainer.py:125-141).
+// Weights are the canonical Keras tensors W[in][out], b[out]; dff a multiple of 128, at most 512.
+struct DecChainArgs {
+  const float* dec_input; int F;                 // [C][F]
+  const float* y_in;                             // [C][128] input of a layer > 0, nullptr for the first one
+  const float *Wemb, *bemb;
+  const float *Wv1, *bv1, *Wo1, *bo1, *g1, *be1;
+  const float *Wq2, *bq2, *Wo2, *bo2, *g2, *be2;
+  const float *Wf1, *bf1, *Wf2, *bf2, *g3, *be3; int dff;
+  const float *Wp1, *bp1;
+  const float* kvw;                              // [C * S][384]: K2 | V2 | W2e of the compact tokens
+  const float* mask; int S; TokWin win;          // mha mask (C, win.Sfull or S)
+  float *y0, *v1, *o1, *rstd1, *q2, *pc, *ctx, *o2, *rstd2, *f, *o3, *rstd3, *w1d;
+  int C; float ln_eps;
+};
+int decoder_chain_fwd(const DecChainArgs& a, cudaStream_t st);
+
 // Pointer head (actor/pointer_attention.py:40-66): w1d[C][128] = W1 dec + b, W2e = kvw[:, 256:384];
 // score (pre-clip), logits (= C*tanh(score) - mask*1e9), probs = softmax(logits), argmax(probs).
 int pointer_fwd(const float* w1d, const float* kvw, const float* V, const float* bV, float clipC, int has_clip,

@@ -232,6 +232,242 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(const float* __rest
   if (half == 0) dq2[(size_t)c * 128 + h * 16 + d] = tf32_rn(acc * 0.25f);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// fused one-token decoder layer (see DecChainArgs in kernels.cuh): 2 * EPL states per CTA, 256 threads.
+// Thread (grp = tid >> 7, col = tid & 127) owns output column `col` of the EPL states grp * EPL .. of the CTA; the
+// weight matrices stream through the CTA once per layer (EPL = 4 for the update's large batches halves that traffic,
+// EPL = 2 keeps more CTAs in flight for the rollout's small ones).
+// ------------------------------------------------------------------------------------------------------
+constexpr int DC_MAX_DFF = 512;
+
+// acc[j] += sum_k x[j][k] * W[k][col]  (W row-major with leading dimension ldw; x rows in shared memory, stride xs_ld)
+template <int EPL>
+__device__ __forceinline__ void dc_gemv(const float* __restrict__ W, int ldw, int K, const float* x, int xs_ld,
+                                        float (&acc)[EPL]) {
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(W + (size_t)k * ldw);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) acc[j] = fmaf(x[j * xs_ld + k], w, acc[j]);
+  }
+}
+
+// LayerNorm of the EPL rows a thread group holds one column of each: the arithmetic of the GEMM epilogue (two-pass
+// mean / variance, biased variance, eps inside the square root). red: [2 groups][4 warps][EPL rows].
+template <int EPL>
+__device__ __forceinline__ void dc_layernorm(const float (&t)[EPL], float gamma, float beta, float eps,
+                                             float (*red)[4][4], int grp, int wg, int lane, float (&o)[EPL],
+                                             float (&r)[EPL]) {
+  float s[EPL], d[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) s[j] = warp_sum(t[j]);
+  __syncthreads();                       // red is free (its previous readers are past this point)
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) red[grp][wg][j] = s[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const float m = (red[grp][0][j] + red[grp][1][j] + red[grp][2][j] + red[grp][3][j]) * (1.0f / 128.0f);
+    d[j] = t[j] - m;
+    s[j] = warp_sum(d[j] * d[j]);
+  }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) red[grp][wg][j] = s[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    r[j] = 1.0f / sqrtf((red[grp][0][j] + red[grp][1][j] + red[grp][2][j] + red[grp][3][j]) * (1.0f / 128.0f) + eps);
+    o[j] = d[j] * r[j] * gamma + beta;
+  }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(256) decoder_chain_kernel(const DecChainArgs a) {
+  constexpr int EPC = 2 * EPL;
+  __shared__ float xs[EPC][128];               // the layer's running vector (y, o1, o2, o3)
+  __shared__ float ys[EPC][128];               // v1, q2
+  __shared__ float hs[EPC][DC_MAX_DFF];        // ctx, then the FFN hidden
+  __shared__ float ps[8][XA_MAX_S];            // cross-attention scores / probabilities of one state
+  __shared__ float red[2][4][4];
+  const int tid = threadIdx.x, col = tid & 127, grp = tid >> 7, warp = tid >> 5, lane = tid & 31, wg = warp & 3;
+  const int el = grp * EPL;                    // first local state of this thread
+  const int cb = blockIdx.x * EPC + el;        // its global index
+  bool ok[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) ok[j] = cb + j < a.C;
+  auto put = [&](float* dst, int ld, int off, const float (&v)[EPL]) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (ok[j]) dst[(size_t)(cb + j) * ld + off] = v[j];
+  };
+  auto put_row = [&](float* dst, const float (&v)[EPL]) {   // one value per state (rstd)
+    if (col == 0)
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        if (ok[j]) dst[cb + j] = v[j];
+  };
+
+  // ---- input of the layer
+  float y[EPL];
+  if (a.y_in) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) y[j] = ok[j] ? a.y_in[(size_t)(cb + j) * 128 + col] : 0.f;
+  } else {   // decoder embedding: products accumulated onto the bias in feature order (small_dense_fwd_kernel)
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) y[j] = __ldg(a.bemb + col);
+    for (int f = 0; f < a.F; ++f) {
+      const float w = __ldg(a.Wemb + (size_t)f * 128 + col);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) y[j] = fmaf(ok[j] ? a.dec_input[(size_t)(cb + j) * a.F + f] : 0.f, w, y[j]);
+    }
+    put(a.y0, 128, col, y);
+  }
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) xs[el + j][col] = y[j];
+  __syncthreads();
+
+  // ---- mha1 with a single key: attn1 = Dense_o1(Dense_v1(y))
+  float t[EPL], o[EPL], r[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bv1 + col);
+  dc_gemv<EPL>(a.Wv1 + col, 128, 128, &xs[el][0], 128, t);
+  put(a.v1, 128, col, t);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) ys[el + j][col] = t[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bo1 + col);
+  dc_gemv<EPL>(a.Wo1 + col, 128, 128, &ys[el][0], 128, t);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] += y[j];
+  dc_layernorm<EPL>(t, __ldg(a.g1 + col), __ldg(a.be1 + col), a.ln_eps, red, grp, wg, lane, o, r);
+  put(a.o1, 128, col, o);
+  put_row(a.rstd1, r);
+  float o1v[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) o1v[j] = o[j];
+  __syncthreads();                       // every read of xs (y) is done
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) xs[el + j][col] = o1v[j];
+  __syncthreads();
+
+  // ---- mha2: the query
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bq2 + col);
+  dc_gemv<EPL>(a.Wq2 + col, 128, 128, &xs[el][0], 128, t);
+  put(a.q2, 128, col, t);
+  __syncthreads();                       // reads of ys (v1) are done
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) ys[el + j][col] = t[j];
+  __syncthreads();
+
+  // ---- cross attention, one state at a time: warp == head (the arithmetic of cross_attn_fwd_kernel)
+  const int S = a.S, Sf = a.win.Sfull > 0 ? a.win.Sfull : S;
+  for (int e = 0; e < EPC; ++e) {
+    const int c = blockIdx.x * EPC + e;
+    if (c >= a.C) break;                 // uniform over the CTA
+    const int h = warp;
+    const float* kv = a.kvw + (size_t)c * S * 384;
+    float q[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) q[d] = ys[e][h * 16 + d];
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      const float4* kr = reinterpret_cast<const float4*>(kv + (size_t)j * 384 + h * 16);
+      float sc = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 k = kr[d4];
+        sc = fmaf(q[d4 * 4 + 0], k.x, sc); sc = fmaf(q[d4 * 4 + 1], k.y, sc);
+        sc = fmaf(q[d4 * 4 + 2], k.z, sc); sc = fmaf(q[d4 * 4 + 3], k.w, sc);
+      }
+      sc = sc * 0.25f + a.mask[(size_t)c * Sf + a.win.full(j)] * -BIG_NUMBER;   // / sqrt(16), + mask * -1e9 (common/utils.py:34-38)
+      ps[h][j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float ex = expf(ps[h][j] - mx);
+      ps[h][j] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < S; j += 32) {
+      const float p = ps[h][j] * inv;
+      ps[h][j] = p;
+      a.pc[((size_t)c * 8 + h) * S + j] = p;
+    }
+    __syncwarp();
+    const int d = lane & 15, half = lane >> 4;
+    float acc = 0.f;
+    for (int j = half; j < S; j += 2) acc = fmaf(ps[h][j], kv[(size_t)j * 384 + 128 + h * 16 + d], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (half == 0) {
+      a.ctx[(size_t)c * 128 + h * 16 + d] = acc;
+      hs[e][h * 16 + d] = acc;           // hs doubles as the ctx buffer until the FFN needs it
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- mha2 output projection + LayerNorm 2
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bo2 + col);
+  dc_gemv<EPL>(a.Wo2 + col, 128, 128, &hs[el][0], DC_MAX_DFF, t);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] += o1v[j];
+  dc_layernorm<EPL>(t, __ldg(a.g2 + col), __ldg(a.be2 + col), a.ln_eps, red, grp, wg, lane, o, r);
+  put(a.o2, 128, col, o);
+  put_row(a.rstd2, r);
+  float o2v[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) o2v[j] = o[j];
+  __syncthreads();                       // reads of xs (o1) and hs (ctx) are done
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) xs[el + j][col] = o2v[j];
+  __syncthreads();
+
+  // ---- FFN
+  for (int jt = 0; jt < a.dff; jt += 128) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bf1 + jt + col);
+    dc_gemv<EPL>(a.Wf1 + jt + col, a.dff, 128, &xs[el][0], 128, t);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      t[j] = fmaxf(t[j], 0.f);
+      hs[el + j][jt + col] = t[j];
+    }
+    put(a.f, a.dff, jt + col, t);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bf2 + col);
+  dc_gemv<EPL>(a.Wf2 + col, 128, a.dff, &hs[el][0], DC_MAX_DFF, t);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) t[j] += o2v[j];
+  dc_layernorm<EPL>(t, __ldg(a.g3 + col), __ldg(a.be3 + col), a.ln_eps, red, grp, wg, lane, o, r);
+  put(a.o3, 128, col, o);
+  put_row(a.rstd3, r);
+
+  // ---- pointer: W1 dec (last layer)
+  if (a.Wp1) {
+    __syncthreads();                     // reads of xs (o2) are done
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) xs[el + j][col] = o[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) t[j] = __ldg(a.bp1 + col);
+    dc_gemv<EPL>(a.Wp1 + col, 128, 128, &xs[el][0], 128, t);
+    put(a.w1d, 128, col, t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // pointer head: one CTA (8 warps) per state; warp per key, lane holds 4 of the 128 units
 // ------------------------------------------------------------------------------------------------------
@@ -473,6 +709,15 @@ int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const f
   if (C <= 0) return TPC_OK;
   if (S > XA_MAX_S) return TPC_ERR_SHAPE;
   cross_attn_bwd_kernel<<<C, 256, 0, st>>>(dctx, q2, kvw, pc, S, dq2, dkvw);
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
+int decoder_chain_fwd(const DecChainArgs& a, cudaStream_t st) {
+  if (a.C <= 0) return TPC_OK;
+  if (a.S > XA_MAX_S || a.dff % 128 != 0 || a.dff < 128 || a.dff > DC_MAX_DFF) return TPC_ERR_SHAPE;
+  if (a.C >= 4096) decoder_chain_kernel<4><<<ceil_div(a.C, 8), 256, 0, st>>>(a);
+  else decoder_chain_kernel<2><<<ceil_div(a.C, 4), 256, 0, st>>>(a);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

@@ -285,10 +285,10 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
   TokWin win;
   win.N = N; win.gap = r0; win.Sfull = N + R;
   a.y0 = ar.f((size_t)C * 128);
-  RUN(small_dense_fwd(dec_input, L.demb.in, nullptr, C, RowMap{1, 1, 0}, cx.P + L.demb.w, cx.P + L.demb.b, L.demb.in,
-                      a.y0, cx.st));
   a.dec.resize(nl);
-  const float* y = a.y0;
+  a.w1d = ar.f((size_t)C * 128);
+  a.score = ar.f((size_t)C * S);
+  const float* y = nullptr;                 // first layer: the chain kernel embeds dec_input itself
   for (int i = 0; i < nl; ++i) {
     const DecLayerP& lp = L.dec[i];
     DecLayerActs& d = a.dec[i];
@@ -296,26 +296,28 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
     d.q2 = ar.f((size_t)C * 128); d.kvw = ar.f((size_t)C * S * 384); d.pc = ar.f((size_t)C * 8 * S);
     d.ctx = ar.f((size_t)C * 128); d.o2 = ar.f((size_t)C * 128); d.rstd2 = ar.f(C);
     d.f = ar.f((size_t)C * dff); d.o3 = ar.f((size_t)C * 128); d.rstd3 = ar.f(C);
-    // mha1 on a single token: softmax over one key == 1 => attn1 = dense(wv(y)) (actor/decoder_layer.py:22)
-    TPC_TRY(gemm_fwd(cx, y, 128, cx.W + lp.s.wv1_t, 128, d.v1, 128, C, 128, 128, epi_bias(cx.P + lp.mha1.v.b)));
-    TPC_TRY(gemm_fwd(cx, d.v1, 128, cx.W + lp.s.wo1_t, 128, d.o1, 128, C, 128, 128,
-                 epi_ln(cx, cx.P + lp.mha1.o.b, y, lp.ln1, d.rstd1)));
-    TPC_TRY(gemm_fwd(cx, d.o1, 128, cx.W + lp.s.wq2_t, 128, d.q2, 128, C, 128, 128, epi_bias(cx.P + lp.mha2.q.b)));
+    // K2 | V2 | W2e of every encoder token: the one GEMM-shaped product of the decoder (tensor cores, 3xTF32)
     TPC_TRY(gemm_fwd(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
                  epi_bias(cx.W + lp.s.bkvp)));
-    RUN(cross_attn_fwd(d.q2, d.kvw, mha_mask, C, S, d.ctx, d.pc, cx.st, win));
-    TPC_TRY(gemm_fwd(cx, d.ctx, 128, cx.W + lp.s.wo2_t, 128, d.o2, 128, C, 128, 128,
-                 epi_ln(cx, cx.P + lp.mha2.o.b, d.o1, lp.ln2, d.rstd2)));
-    GemmEpi e1 = epi_bias(cx.P + lp.f1.b);
-    e1.relu = 1;
-    TPC_TRY(gemm_fwd(cx, d.o2, 128, cx.W + lp.s.w1_t, 128, d.f, dff, C, dff, 128, e1));
-    TPC_TRY(gemm_fwd(cx, d.f, dff, cx.W + lp.s.w2_t, dff, d.o3, 128, C, 128, dff,
-                 epi_ln(cx, cx.P + lp.f2.b, d.o2, lp.ln3, d.rstd3)));
+    // everything on the single decoder token: one fused kernel (csrc/kernels.cuh, DecChainArgs)
+    DecChainArgs ca{};
+    ca.dec_input = dec_input; ca.F = L.demb.in; ca.y_in = y;
+    ca.Wemb = cx.P + L.demb.w; ca.bemb = cx.P + L.demb.b;
+    ca.Wv1 = cx.P + lp.mha1.v.w; ca.bv1 = cx.P + lp.mha1.v.b; ca.Wo1 = cx.P + lp.mha1.o.w; ca.bo1 = cx.P + lp.mha1.o.b;
+    ca.g1 = cx.P + lp.ln1.g; ca.be1 = cx.P + lp.ln1.b;
+    ca.Wq2 = cx.P + lp.mha2.q.w; ca.bq2 = cx.P + lp.mha2.q.b; ca.Wo2 = cx.P + lp.mha2.o.w; ca.bo2 = cx.P + lp.mha2.o.b;
+    ca.g2 = cx.P + lp.ln2.g; ca.be2 = cx.P + lp.ln2.b;
+    ca.Wf1 = cx.P + lp.f1.w; ca.bf1 = cx.P + lp.f1.b; ca.Wf2 = cx.P + lp.f2.w; ca.bf2 = cx.P + lp.f2.b; ca.dff = dff;
+    ca.g3 = cx.P + lp.ln3.g; ca.be3 = cx.P + lp.ln3.b;
+    const bool last = i == nl - 1;
+    ca.Wp1 = last ? cx.P + L.W1.w : nullptr; ca.bp1 = last ? cx.P + L.W1.b : nullptr;
+    ca.kvw = d.kvw; ca.mask = mha_mask; ca.S = S; ca.win = win;
+    ca.y0 = a.y0; ca.v1 = d.v1; ca.o1 = d.o1; ca.rstd1 = d.rstd1; ca.q2 = d.q2; ca.pc = d.pc; ca.ctx = d.ctx;
+    ca.o2 = d.o2; ca.rstd2 = d.rstd2; ca.f = d.f; ca.o3 = d.o3; ca.rstd3 = d.rstd3; ca.w1d = a.w1d;
+    ca.C = C; ca.ln_eps = 1e-6f;
+    RUN(decoder_chain_fwd(ca, cx.st));
     y = d.o3;
   }
-  a.w1d = ar.f((size_t)C * 128);
-  a.score = ar.f((size_t)C * S);
-  TPC_TRY(gemm_fwd(cx, y, 128, cx.W + L.w1p_t, 128, a.w1d, 128, C, 128, 128, epi_bias(cx.P + L.W1.b)));
   if (fuse) {
     fuse->w1d = a.w1d; fuse->kvw = a.dec[nl - 1].kvw; fuse->V = cx.P + L.V.w; fuse->bV = cx.P + L.V.b;
     fuse->clipC = cx.m->dims.clip_C; fuse->has_clip = cx.m->dims.has_clip; fuse->ptr_mask = ptr_mask;
