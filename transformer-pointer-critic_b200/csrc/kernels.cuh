@@ -49,11 +49,8 @@ int attention_fwd(const float* qkv, const float* mask, int mS, int m0, int C, in
 int attention_bwd(const float* qkv, const float* att, const float* lse, const float* datt, const float* mask, int mS,
                   int m0, int C, int L, float* dqkv, cudaStream_t st, int mask_split = 1 << 30, int mask_gap = 0);
 
-// Decoder cross attention with ONE query per state (actor/decoder_layer.py:26-27): q2[C][128],
-// kvw[C*S][384] (K2 | V2 | W2e), mask[C][S] -> ctx[C][128], probs pc[C][8][S]
-// S = compact tokens per state; the mask row of state c is mask[c * w.Sfull + w.full(j)] (w.Sfull == 0: S, identity)
-int cross_attn_fwd(const float* q2, const float* kvw, const float* mask, int C, int S, float* ctx, float* pc,
-                   cudaStream_t st, TokWin w = TokWin());
+// Backward of the decoder cross attention with ONE query per state (actor/decoder_layer.py:26-27; the forward is
+// part of decoder_chain_fwd): q2[C][128], kvw[C*S][384] (K2 | V2 | W2e), probs pc[C][8][S] ->
 // dq2[C][128], dkvw[:, 0:256]
 int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const float* pc, int C, int S, float* dq2,
                    float* dkvw, cudaStream_t st);

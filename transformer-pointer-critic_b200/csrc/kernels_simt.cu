@@ -131,54 +131,6 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, int rows, Row
 // ------------------------------------------------------------------------------------------------------
 constexpr int XA_MAX_S = 512;
 
-__global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __restrict__ q2, const float* __restrict__ kvw,
-                                                             const float* __restrict__ mask, int S,
-                                                             float* __restrict__ ctx, float* __restrict__ pc, TokWin w) {
-  __shared__ float ps[8][XA_MAX_S];
-  const int c = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* kv = kvw + (size_t)c * S * 384;
-  float q[16];
-#pragma unroll
-  for (int d4 = 0; d4 < 4; ++d4) {
-    const float4 t = reinterpret_cast<const float4*>(q2 + (size_t)c * 128 + h * 16)[d4];
-    q[d4 * 4 + 0] = t.x; q[d4 * 4 + 1] = t.y; q[d4 * 4 + 2] = t.z; q[d4 * 4 + 3] = t.w;
-  }
-  float mx = -INFINITY;
-  for (int j = lane; j < S; j += 32) {
-    const float4* kr = reinterpret_cast<const float4*>(kv + (size_t)j * 384 + h * 16);
-    float s = 0.f;
-#pragma unroll
-    for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 k = kr[d4];
-      s = fmaf(q[d4 * 4 + 0], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
-      s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
-    }
-    s = s * 0.25f + mask[(size_t)c * (w.Sfull > 0 ? w.Sfull : S) + w.full(j)] * -BIG_NUMBER;  // / sqrt(16), + mask * -1e9 (common/utils.py:34-38)
-    ps[h][j] = s;
-    mx = fmaxf(mx, s);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < S; j += 32) {
-    const float e = expf(ps[h][j] - mx);
-    ps[h][j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
-  for (int j = lane; j < S; j += 32) {
-    const float p = ps[h][j] * inv;
-    ps[h][j] = p;
-    pc[((size_t)c * 8 + h) * S + j] = p;
-  }
-  __syncwarp();
-  const int d = lane & 15, half = lane >> 4;
-  float acc = 0.f;
-  for (int j = half; j < S; j += 2) acc = fmaf(ps[h][j], kv[(size_t)j * 384 + 128 + h * 16 + d], acc);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  if (half == 0) ctx[(size_t)c * 128 + h * 16 + d] = acc;
-}
-
 __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(const float* __restrict__ dctx, const float* __restrict__ q2,
                                                              const float* __restrict__ kvw, const float* __restrict__ pc,
                                                              int S, float* __restrict__ dq2, float* __restrict__ dkvw) {
@@ -365,7 +317,7 @@ __global__ void __launch_bounds__(256) decoder_chain_kernel(const DecChainArgs a
   for (int j = 0; j < EPL; ++j) ys[el + j][col] = t[j];
   __syncthreads();
 
-  // ---- cross attention, one state at a time: warp == head (the arithmetic of cross_attn_fwd_kernel)
+  // ---- cross attention, one state at a time: warp == head (one query per state, actor/decoder_layer.py:26-27)
   const int S = a.S, Sf = a.win.Sfull > 0 ? a.win.Sfull : S;
   for (int e = 0; e < EPC; ++e) {
     const int c = blockIdx.x * EPC + e;
@@ -691,15 +643,6 @@ int colsum(const float* dY, int ld, int M, int N, float* db, cudaStream_t st) {
 int scatter_rows(const float* src, int rows, RowMap map, float* dst, cudaStream_t st) {
   if (rows <= 0) return TPC_OK;
   scatter_rows_kernel<<<blocks_for((long long)rows * 32, 256), 256, 0, st>>>(src, rows, map, dst);
-  TPC_CHECK_LAUNCH();
-  return TPC_OK;
-}
-
-int cross_attn_fwd(const float* q2, const float* kvw, const float* mask, int C, int S, float* ctx, float* pc,
-                   cudaStream_t st, TokWin w) {
-  if (C <= 0) return TPC_OK;
-  if (S > XA_MAX_S) return TPC_ERR_SHAPE;
-  cross_attn_fwd_kernel<<<C, 256, 0, st>>>(q2, kvw, mask, S, ctx, pc, w);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
