@@ -56,7 +56,7 @@ int cross_attn_bwd(const float* dctx, const float* q2, const float* kvw, const f
                    float* dkvw, cudaStream_t st);
 
 // One decoder layer on the single decoder token of every state (actor/decoder.py:74-81, actor/decoder_layer.py:18-32) as
-// ONE kernel, 4 states per CTA, fp32 FMA on CUDA cores (the products are [4 x 128] x [128 x 128]: GEMV-sized, a
+// ONE kernel, 2 (rollout) or 8 (update) states per CTA, fp32 FMA on CUDA cores (the products are GEMV-sized: a
 // 148-CTA tensor-core launch each would cost more in launch latency than in arithmetic):
 //   [y0 = Dense_emb(dec_input)]                          first layer only (y_in == nullptr)
 //   v1 = Dense_v1(y); o1 = LN1(Dense_o1(v1) + y)          mha1 over one key: softmax == 1

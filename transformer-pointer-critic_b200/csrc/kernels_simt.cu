@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------------
 // fused one-token decoder layer (see DecChainArgs in kernels.cuh): 2 * EPL states per CTA, 256 threads.
 // Thread (grp = tid >> 7, col = tid & 127) owns output column `col` of the EPL states grp * EPL .. of the CTA; the
-// weight matrices stream through the CTA once per layer (EPL = 4 for the update's large batches halves that traffic,
-// EPL = 2 keeps more CTAs in flight for the rollout's small ones).
+// weight matrices stream through the CTA once per layer (EPL = 4 for the update's large batches: a quarter of the L2
+// traffic; EPL = 1 for the rollout's small ones: more CTAs in flight, the cross-attention of a CTA's states is serial).
 // ------------------------------------------------------------------------------------------------------
 constexpr int DC_MAX_DFF = 512;
 
@@ -660,7 +660,7 @@ int decoder_chain_fwd(const DecChainArgs& a, cudaStream_t st) {
   if (a.C <= 0) return TPC_OK;
   if (a.S > XA_MAX_S || a.dff % 128 != 0 || a.dff < 128 || a.dff > DC_MAX_DFF) return TPC_ERR_SHAPE;
   if (a.C >= 4096) decoder_chain_kernel<4><<<ceil_div(a.C, 8), 256, 0, st>>>(a);
-  else decoder_chain_kernel<2><<<ceil_div(a.C, 4), 256, 0, st>>>(a);
+  else decoder_chain_kernel<1><<<ceil_div(a.C, 2), 256, 0, st>>>(a);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }
