@@ -72,24 +72,33 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def dataflow_bytes_per_state(N, R, actor=(1, 128), critic=(3, 512), d=128):
+def dataflow_bytes_per_state(N, R, B=1024, chunk=10240, actor=(1, 128), critic=(3, 512), d=128):
     """HBM bytes one stored state moves through the UPDATE in the current kernel decomposition,
     counted in units of one [token, 128] fp32 row (512 B) per encoder token-layer with dff = m * 128:
       forward  : QKV 1+3, attention 3+1, O-proj + LN 1+1+1, FFN1 1+m, FFN2 + LN m+1+1             = 14 + 2m
       backward : 2 x LN 3, dW2 m+1, dH 1+m, dW1 1+m, d(out1) m+1+1, dWo 2, d(att) 2, attention 3+1+1+3, dWqkv 1+3,
                  dx 3+1+1                                                                          = 32 + 4m
-    times (N + R) tokens x 2 (bins + resources stacks, then the joint stack) x layers, critic + actor (the actor's
-    decoder / pointer add (2 * 3 + 3 * 3) rows per token once). The rollout adds one actor forward per decision."""
-    S = N + R
+    times the tokens of the three stacks (bins N, rules R, joint N + R) x layers. The critic keeps every token; the
+    actor leaves out the rule tokens placed before the first step of its chunk (token windows): chunk k of `chunk`
+    states drops floor(k * chunk / B) rules, the rollout step t drops t. The actor's decoder adds the K2|V2|W2e
+    projection of its tokens (1 + 3 forward, 3 + 1 + 1 + 3 backward rows per token)."""
     u = d * 4
-    total = 0
-    for layers, dff in (critic, actor):
+    T = R
+    n_chunks = max(1, -(-T * B // chunk))
+    kept_update = sum(R - min(R - 1, (k * chunk) // B) for k in range(n_chunks)) / n_chunks
+    kept_rollout = sum(R - t for t in range(T)) / T
+
+    def encoder(layers, dff, rules):
         m = dff // d
-        total += 2 * S * layers * ((14 + 2 * m) + (32 + 4 * m)) * u
-    total += S * 15 * u                                   # K2|V2|W2 projection of the decoder, forward + backward
-    m = actor[1] // d
-    rollout = 2 * S * actor[0] * (14 + 2 * m) * u + S * 4 * u
-    return total, rollout
+        tokens = N + rules + (N + rules)                      # bins stack + rules stack + joint stack
+        return tokens * layers, (14 + 2 * m), (32 + 4 * m)
+    tl, f, b = encoder(*critic, R)
+    total = tl * (f + b) * u
+    tl, f, b = encoder(*actor, kept_update)
+    total += tl * (f + b) * u + (N + kept_update) * 12 * u
+    tl, f, b = encoder(*actor, kept_rollout)
+    rollout = tl * f * u + (N + kept_rollout) * 4 * u
+    return int(total), int(rollout)
 
 
 CPU_EPISODES = 32
@@ -395,8 +404,8 @@ def run_ours(args):
         "config": {"workload": f"ResourceV3 {nodes} nodes x {rules} rules, batch {B}/GPU, {args.reward} reward, rollout + A2C "
                                f"update (actor 1 layer, critic 3 layers)",
                    "decisions_per_step": world * B * T, "chunk_states": chunk,
-                   "hbm_bytes_per_state": {"update": dataflow_bytes_per_state(N, R)[0],
-                                           "rollout": dataflow_bytes_per_state(N, R)[1],
+                   "hbm_bytes_per_state": {"update": dataflow_bytes_per_state(N, R, B, chunk)[0],
+                                           "rollout": dataflow_bytes_per_state(N, R, B, chunk)[1],
                                            "note": "modelled from the kernel decomposition (bench.py "
                                                    "dataflow_bytes_per_state), not a counter"},
                    "l2": "working set per step (>4 GB of activations) far exceeds the 126 MB L2; no flush needed",
