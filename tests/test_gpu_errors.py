@@ -122,3 +122,106 @@ def test_ragged_instances_single_node_and_all_rejected(ctx):
         np.testing.assert_array_equal(s.solution.remaining.cpu().numpy()[0, 1:], full[0, 1:3])
         oa, orem = oh.dominant_heuristic(full[0], 3, True, True)
         assert oa.tolist() == [0, 0, 0, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model path: smallest / odd / largest shapes of the actor, the fused rollout and the update
+# ---------------------------------------------------------------------------------------------------------------------
+def _agent(N_nodes, R, B, reward="greedy"):
+    import json
+    from tpc_b200.agent import Agent
+    from tpc_b200.configs import get_configs
+    from tpc_b200.env import ResourceEnvironmentV3
+    agent_cfg, _, env_cfg, _, _, _ = get_configs("ResourceV3", "tpc")
+    env_cfg = json.loads(json.dumps(env_cfg))
+    env_cfg.update(batch_size=B, node_sample_size=N_nodes, profiles_sample_size=R)
+    env_cfg["reward"]["type"] = reward
+    env = ResourceEnvironmentV3("ResourceV3", env_cfg, DEV)
+    agent_cfg = env.add_stats_to_agent_config(json.loads(json.dumps(agent_cfg)))
+    return env, Agent("transformer", agent_cfg, DEV, num_features=3, seed=7)
+
+
+@pytest.mark.parametrize("nodes,rules,B", [(1, 1, 1), (1, 3, 3), (3, 2, 5), (10, 20, 7)])
+def test_smallest_and_odd_shapes_train_one_iteration(nodes, rules, B):
+    """One real node / one rule / batches that fill no CTA of the decoder chain (2 or 8 states per CTA) and no GEMM tile:
+    the rollout replays bit-exactly through the oracle env, logits match the oracle model, the update stays finite."""
+    import torch
+    from oracle import model as om
+    from oracle.env import ResourceV3Oracle
+    env, agent = _agent(nodes, rules, B)
+    N, R, S = nodes + 1, rules, nodes + 1 + rules
+    bufs = env.device_buffers(store=True, keep_logits=True)
+    env.reset_into(bufs)
+    init = bufs.batch.cpu().numpy().copy()
+    agent.rollout(env, bufs, greedy=True)
+    torch.cuda.synchronize()
+    cfg = dict(env.opts)
+    ora = ResourceV3Oracle(cfg)
+    state, dec, bm, mh = ora.load(init)
+    fa = torch.tensor(agent.bin_actor.get_flat())
+    ca = om.NetCfg(num_layers=1, dff=128)
+    for t in range(R):
+        feas = ora.build_feasible_mask(state, dec, bm)
+        assert np.array_equal(bufs.states[t].cpu().numpy(), state) and np.array_equal(bufs.ptr_masks[t].cpu().numpy(), feas)
+        ol, _, oi = om.actor_forward(fa, ca, torch.tensor(state), torch.tensor(dec), torch.tensor(feas), torch.tensor(mh), N)
+        unm = feas == 0
+        cl = bufs.logits[t].cpu().numpy()
+        assert np.abs(cl[unm] - ol.numpy()[unm]).max() <= 1e-3 * max(1.0, np.abs(ol.numpy()[unm]).max())
+        assert np.all(cl[~unm] == -1e9)
+        a = bufs.actions[t].cpu().numpy()
+        state, dec, rw, done, info = ora.step(a, feas)
+        assert np.array_equal(bufs.rewards[:, t].cpu().numpy(), np.asarray(rw, np.float32).reshape(B))
+        bm, mh = info["bin_net_mask"], info["mha_used_mask"]
+    assert done
+    losses = agent.update(bufs).cpu().numpy()
+    assert np.all(np.isfinite(losses))
+    assert np.all(np.isfinite(agent.bin_actor.get_flat())) and np.all(np.isfinite(agent.critic.get_flat()))
+
+
+def test_largest_sequence_and_refusal_beyond_it():
+    """S = 512 tokens is the limit of the one-query kernels (cross-attention, pointer head): it runs and matches the
+    oracle; one token more is refused with TPC_ERR_SHAPE (surfaced as TpcError), not mis-computed."""
+    import torch
+    from oracle import model as om
+    from tpc_b200.lib import TpcError
+    rng = np.random.default_rng(3)
+    for N, R, ok in ((112, 400, True), (113, 400, False)):
+        env, agent = _agent(N - 1, R, 2)
+        S = N + R
+        state = rng.integers(0, 100, size=(2, S, 3)).astype(np.float32) / 100
+        state[:, 0] = -2
+        dec = state[:, N:N + 1].copy()
+        pm = np.zeros((2, S), np.float32)
+        pm[:, N:] = 1
+        mh = np.zeros((2, 1, 1, S), np.float32)
+        mh[:, :, :, N:N + 7] = 1
+        if not ok:
+            with pytest.raises(TpcError):
+                agent.bin_actor(state, dec, pm, True, N, enc_padding_mask=mh, dec_padding_mask=mh)
+            continue
+        lg, pr, idx, _ = agent.bin_actor(state, dec, pm, True, N, enc_padding_mask=mh, dec_padding_mask=mh)
+        ol, op, oi = om.actor_forward(torch.tensor(agent.bin_actor.get_flat()), om.NetCfg(num_layers=1, dff=128),
+                                      torch.tensor(state), torch.tensor(dec), torch.tensor(pm), torch.tensor(mh), N)
+        unm = pm == 0
+        assert np.abs(np.asarray(lg)[unm] - ol.numpy()[unm]).max() < 1e-3 * np.abs(ol.numpy()[unm]).max()
+        assert np.abs(np.asarray(pr) - op.numpy()).max() < 1e-3
+
+
+def test_cvrp_smallest_and_empty(ctx):
+    lib, h, st, L, torch = ctx
+    from tpc_b200.env import CVRP
+    env = CVRP("CVRP", {"batch_size": 3, "node_sample_size": 2, "vehicle_sample_size": 1, "num_features": 3})
+    state, bp, item, mha = env.reset()
+    assert state.shape == (3, 3, 3) and env.steps == 2
+    feas = env.build_feasible_mask(state, state[:, 1], bp)
+    assert feas.tolist() == [[1.0, 1.0, 0.0]] * 3
+    state, r, done, info = env.step([2, 2, 2], [1, 1, 1])
+    assert not done and np.all(np.asarray(r) <= 0) and np.all(info["item_net_mask"][:, 0] == 0)     # the depot opens
+    state, r, done, info = env.step([2, 2, 2], [0, 0, 0])
+    assert done and np.all(info["backpack_net_mask"] == 1)
+    x = torch.zeros(1, 3, 3, device=DEV)
+    m = torch.zeros(1, 3, device=DEV)
+    i = torch.zeros(1, dtype=torch.int32, device=DEV)
+    assert lib.tpc_cvrp_step(h, L.ptr(x), L.ptr(m), L.ptr(m), L.ptr(m), L.ptr(i), L.ptr(i), 0, 2, 1, 0, L.ptr(m), st) == OK
+    assert lib.tpc_cvrp_reset(h, 1, 0, 0, 1, 1, 1, 24, 100, L.ptr(x), L.ptr(m), L.ptr(m), L.ptr(m), st) == ERR_SHAPE
+    assert lib.tpc_cvrp_feasible_mask(h, None, L.ptr(x), L.ptr(m), 1, 3, L.ptr(m), st) == ERR_ARG
