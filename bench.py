@@ -149,7 +149,7 @@ def run_reference(args):
 
 def roofline_probe(lib, h, st, M, dev):
     """The launch of the dominant kernel that the roofline is quoted on: gemm_tc_kernel as the critic's second FFN
-    layer (K = 512 -> 128, 3xTF32) with the residual add + LayerNorm epilogue, M tokens of one update chunk.
+    layer (K = 512 -> 128, fp32-accurate FP16-split product) with the residual add + LayerNorm epilogue, M tokens of one update chunk.
     Returns (callable, algorithmic bytes per launch, label). tests/gpu_checks/roofline_probe.py runs the same
     launch under ncu for `profiles/gemm_tc_traffic.json`."""
     import torch
@@ -157,7 +157,8 @@ def roofline_probe(lib, h, st, M, dev):
     K = 512
     A = torch.randn(M, K, device=dev)
     W = torch.randn(128, K, device=dev) / K ** 0.5
-    Wlo = W - (W.view(torch.int32) & -8192).view(torch.float32)
+    Wlo = torch.empty_like(W)   # bf16 correction image of the weights (tpc.h: tpc_gemm_split_image)
+    L.check(lib.tpc_gemm_split_image(h, L.ptr(W), K, 128, K, L.ptr(Wlo), st))
     res = torch.randn(M, 128, device=dev)
     D = torch.empty(M, 128, device=dev)
     g = torch.ones(128, device=dev)
@@ -170,7 +171,7 @@ def roofline_probe(lib, h, st, M, dev):
                              L.ptr(g), L.ptr(b), L.ptr(rstd), 2, 1, L.ptr(Wlo), st))
     # read the activations and the residual once, write the normalised output and 1/sigma once
     alg_bytes = (M * K + M * 128 + M * 128 + M) * 4
-    return call, alg_bytes, "FFN2 512->128 3xTF32 + residual + LayerNorm"
+    return call, alg_bytes, "FFN2 512->128 fp32-accurate (FP16x2 split) + residual + LayerNorm"
 
 
 def run_check(args, world, rank, dev, B, nodes, rules):
@@ -387,7 +388,8 @@ def run_ours(args):
     tensor = {"bound": "tensor", "achieved": step_tflops, "peak": float(tf32.value), "unit": "TFLOP/s",
               "frac": (step_tflops / float(tf32.value)) if step_tflops else None,
               "peak_source": "measured live: tcgen05.mma kind::tf32 M128 N256 K8, operands resident in shared memory, "
-                             "148 CTAs (tpc_tf32_peak_probe); 3xTF32 forward GEMMs issue 3 MMAs per algorithmic one",
+                             "148 CTAs (tpc_tf32_peak_probe); the forward GEMMs issue 3 kind::f16 MMAs (twice the TF32 rate) per "
+                             "algorithmic product, the backward GEMMs one kind::tf32 MMA",
               "flop_per_decision": FLOP_PER_DECISION}
     roofline = {"bound": "hbm", "achieved": alg_bytes / t_gemm / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / t_gemm / 1e9 / hbm_peak, "traffic": traffic,
@@ -399,7 +401,7 @@ def run_ours(args):
         "metric": "ResourceV3 placement decisions/sec (rollout+A2C update)", "value": value, "unit": "decisions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "f32 (3xTF32 forward, TF32 backward)",
+        "dtype": "f32 (forward: fp32-accurate two-term FP16 split products with fp32 accumulation; backward: TF32)",
         "data": "synthetic",
         "config": {"workload": f"ResourceV3 {nodes} nodes x {rules} rules, batch {B}/GPU, {args.reward} reward, rollout + A2C "
                                f"update (actor 1 layer, critic 3 layers)",

@@ -10,16 +10,20 @@ dev = torch.device("cuda:0")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 C_ = int(os.environ.get("CHUNK", 2048))
 M = C_ * 151
+def split_image(Wt):
+    img = torch.empty_like(Wt)
+    L.check(lib.tpc_gemm_split_image(h, L.ptr(Wt), Wt.shape[1], Wt.shape[0], Wt.shape[1], L.ptr(img), st))
+    return img
 A = torch.randn(M, 128, device=dev); W = torch.randn(128, 128, device=dev) / 11
-Wlo = W - (W.view(torch.int32) & -8192).view(torch.float32)
+Wlo = split_image(W)
 D = torch.empty(M, 128, device=dev); res = torch.randn(M, 128, device=dev)
 g = torch.ones(128, device=dev); b = torch.zeros(128, device=dev); rstd = torch.empty(M, device=dev)
 H = torch.randn(M, 512, device=dev); W1 = torch.randn(512, 128, device=dev) / 11
-W1lo = W1 - (W1.view(torch.int32) & -8192).view(torch.float32)
+W1lo = split_image(W1)
 W2 = torch.randn(128, 512, device=dev) / 22
-W2lo = W2 - (W2.view(torch.int32) & -8192).view(torch.float32)
+W2lo = split_image(W2)
 Q = torch.randn(M, 384, device=dev); Wq = torch.randn(384, 128, device=dev) / 11
-Wqlo = Wq - (Wq.view(torch.int32) & -8192).view(torch.float32)
+Wqlo = split_image(Wq)
 dW = torch.zeros(128, 128, device=dev); db = torch.zeros(128, device=dev)
 dW4 = torch.zeros(128, 512, device=dev); db4 = torch.zeros(512, device=dev)
 dW5 = torch.zeros(512, 128, device=dev)

@@ -15,6 +15,15 @@ P = ctypes.c_void_p
 I = ctypes.c_int
 lib.tpc_create.argtypes = [ctypes.POINTER(P)]
 lib.tpc_gemm.argtypes = [P, P, I, P, I, P, I, I, I, I, P, P, I, I, P, P, P, I, I, P, P]
+lib.tpc_gemm_split_image.argtypes = [P, P, I, I, I, P, P]
+
+
+def split_image(h, Bt, stream):
+    """bf16 correction image of the weights (tpc.h: tpc_gemm_split_image), as an fp32-sized buffer"""
+    img = torch.empty_like(Bt)
+    rc = lib.tpc_gemm_split_image(h, ptr(Bt), Bt.shape[1], Bt.shape[0], Bt.shape[1], ptr(img), stream)
+    assert rc == 0, rc
+    return img
 lib.tpc_wgrad.argtypes = [P, P, I, P, I, P, I, P, I, I, I, P]
 
 
@@ -54,7 +63,7 @@ def main():
     for (M, N, K) in [(300, 128, 128), (1000, 384, 128), (4096, 128, 512), (260, 128, 19328)]:
         A = torch.randn(M, K, device=dev)
         Bt = torch.randn(N, K, device=dev) / K ** 0.5
-        Blo = Bt - (Bt.view(torch.int32) & -8192).view(torch.float32)
+        Blo = split_image(h, Bt, stream)
         bias = torch.randn(N, device=dev)
         D = torch.full((M, N), float("nan"), device=dev)
         rc = lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), N, M, N, K, ptr(bias), None, 0, 0, None, None, None, 0, 1,
@@ -71,7 +80,7 @@ def main():
         K = 128
         A = torch.randn(M, K, device=dev)
         Bt = torch.randn(N, K, device=dev) / K ** 0.5
-        Blo = Bt - (Bt.view(torch.int32) & -8192).view(torch.float32)
+        Blo = split_image(h, Bt, stream)
         bias = torch.randn(N, device=dev)
         aux = torch.randn(M, N, device=dev)
         ref0 = A.double() @ Bt.double().T

@@ -10,11 +10,11 @@ dev = torch.device("cuda:0")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 M = 2048 * 151
 A = torch.randn(M, 128, device=dev); W = torch.randn(128, 128, device=dev) / 11
-Wlo = W - (W.view(torch.int32) & -8192).view(torch.float32)
+Wlo = torch.empty_like(W); L.check(lib.tpc_gemm_split_image(h, L.ptr(W), 128, 128, 128, L.ptr(Wlo), st))
 D = torch.empty(M, 128, device=dev); res = torch.randn(M, 128, device=dev)
 g = torch.ones(128, device=dev); b = torch.zeros(128, device=dev); rstd = torch.empty(M, device=dev)
 H = torch.randn(M, 512, device=dev); W1 = torch.randn(512, 128, device=dev) / 11
-W1lo = W1 - (W1.view(torch.int32) & -8192).view(torch.float32)
+W1lo = torch.empty_like(W1); L.check(lib.tpc_gemm_split_image(h, L.ptr(W1), 128, 512, 128, L.ptr(W1lo), st))
 dW = torch.zeros(128, 128, device=dev); db = torch.zeros(128, device=dev)
 for it in range(2):
     # forward projection 3xTF32 + residual + LayerNorm epilogue

@@ -2,6 +2,7 @@
 // PTX wrappers for mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (UMMA + TMEM).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -87,6 +88,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a fully active warp (elect.sync). The MMA-issuing warps run their loops in warp-uniform control flow and
+// only the tcgen05.mma / tcgen05.commit themselves sit behind this predicate: ptxas then keeps the descriptors in
+// uniform registers. Under a thread-private `if (lane == 0)` it cannot prove the operands uniform and wraps EVERY
+// tcgen05.mma in an ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY "waterfall" loop (ncu source page of round 2: three
+// quarters of the issuing thread's samples were those instructions, not the MMAs).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -304,6 +320,36 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor with FP16 operands (a/b format 0; BF16 would be 1), FP32 accumulator
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// Two-term FP16 split of an fp32 value: x = h + r exactly, h = fp16(x) (saturated to the finite range), and r = x - h
+// is then rounded to fp16 itself. Both halves keep 11 bits, so h.h' + h.r' + r.h' reproduces x.x' to ~2^-21; below the
+// fp16 normal range (6e-5) the absolute error of either part is at most 3e-8.
+__device__ __forceinline__ __half f16_hi(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ void f16_split2(float x0, float x1, uint32_t& h, uint32_t& r) {
+  h = pack_f16x2_sat(x0, x1);
+  float h0, h1;
+  asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(h));
+  r = pack_f16x2_sat(x0 - h0, x1 - h1);
+}
+// D[tmem] (+)= A[tmem, 16-bit pairs] . B[smem]^T, M x N x 16
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -8,12 +8,24 @@
 //   common/utils.py:8-11 (FFN), actor/decoder_layer.py:22-30, actor/pointer_attention.py:40-41 (W1/W2),
 //   critic/model.py:65-83 (final_layer0/1) and their backward passes (agents/trainer.py:115-141).
 //
-// Roles in a 256-thread CTA (one CTA per SM, persistent over work items):
-//   warp 0   : TMA producer (A/B k-blocks into a 4-stage smem ring, 128B-swizzled boxes of 32 fp32 columns)
-//   warp 1   : MMA issuer (one elected lane, tcgen05.mma kind::tf32, M=128 N=128 K=8 per instruction)
-//   warp 2   : TMEM allocator (2 x 128 columns: double-buffered accumulator)
+// Two numeric modes:
+//   single pass (backward dX GEMMs, wgrad): tcgen05.mma kind::tf32 on the raw fp32 tiles (SS mode, M=128 N=128 K=8)
+//   split (every forward GEMM; fp32-accurate, ~2^-21 relative): x = x_h + x_r with x_h = fp16(x), x_r = fp16(x - x_h)
+//     and D = A_h.B_h + A_h.B_r + A_r.B_h as three kind::f16 products (K=16) with fp32 accumulation in TMEM. The weight
+//     halves come from a prebuilt fp16 image (build_split_image / the shadow builder), the activation halves are made on
+//     chip by four splitter warps that park them in TMEM (TS-mode MMAs). This replaced 3xTF32 (three kind::tf32 products
+//     on fp32 tiles) in round 2: the B200 runs these launches at its 1000 W power cap (nvidia-smi: sw_power_cap, SM clock
+//     1.3-1.5 GHz under 3xTF32 with random operands, 1.97 GHz with zeros), so tensor-pipe cycles and operand bytes are
+//     paid for in clock rate; the fp16 split needs half the tensor cycles and half the weight bytes per k-block.
+//
+// Roles in gemm_tc_kernel (one persistent CTA of 352 threads per SM; gemm_bres_kernel: 320, no warp 10):
+//   warps 0-3: splitters (split mode): activation k-block smem -> registers -> fp16 halves -> TMEM slot
 //   warps 4-7: epilogue (thread == accumulator row: tcgen05.ld, bias/ReLU/residual/LayerNorm in registers,
-//              swizzled smem staging tile, TMA store)
+//              swizzled smem staging, TMA store)
+//   warp 8   : TMA producer of the activation slots (single pass: of the A + B stages), TMEM allocator
+//   warp 9   : MMA issuer (whole warp in uniform control flow, one elected lane issues), barrier init
+//   warp 10  : TMA producer of the weight slots (split mode)
+#include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 
 #include <map>
@@ -27,18 +39,37 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BK = 32;                        // fp32 columns per k-block == one 128-byte swizzle span
-constexpr int STAGES = 3;                     // 3xTF32 mode: 3 stages of A + B + B_lo (48 KB)
-constexpr int STAGES_1P = 4;                  // single-pass mode: 4 stages of A + B (32 KB) in the same ring space
-constexpr int MAX_STAGES = 4;
+// Ring space of the generic kernel: 160 KB. The HBM latency is hidden by activation bytes in flight, so
+//   split mode:  NA activation slots (16 KB; freed by the splitter warps as soon as the k-block sits in TMEM, NOT by
+//                the MMAs) + NB weight slots (fp16 B_h + B_r, 16 KB, served by L2; freed by the MMA commit)
+//   single-pass: 5 stages of A + B (32 KB), freed by the MMA commit (SS-mode MMAs read A from shared memory)
+#ifndef GEMM_NA
+#define GEMM_NA 6
+#endif
+#ifndef GEMM_NB
+#define GEMM_NB 4
+#endif
+#ifndef BRES_SPLIT_ASTAGES
+#define BRES_SPLIT_ASTAGES 6
+#endif
+#ifndef BRES_SPLIT_EPI_COLS
+#define BRES_SPLIT_EPI_COLS 128
+#endif
+constexpr int NA = GEMM_NA;
+constexpr int NB = GEMM_NB;
+constexpr int NT = 8;                         // TMEM slots of a split k-block (16 + 16 columns of packed halves)
+constexpr int STAGES_1P = 5;
+constexpr int MAX_STAGES = 6;
+constexpr int RING_BYTES = 160 * 1024;
 constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // A + B (+ B_lo in 3xTF32 mode)
+constexpr int BSLOT_BYTES = TILE_BYTES;       // split mode: fp16 B_h + B_r tiles of a k-block (2 x 8 KB)
 constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
 constexpr int GEMM_THREADS = 320;             // warps 0-3 A_lo splitters, 4-7 epilogue, 8 TMA, 9 MMA
+constexpr int GEMM_TC_THREADS = 352;          // generic kernel: + warp 10 = TMA producer of the weight slots (3xTF32)
 constexpr int WG_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
-constexpr int TMEM_COLS = 512;                // 2 x 128 accumulators + STAGES x 32 columns of A_lo
-constexpr int TMEM_ALO = 256;                 // first A_lo column (32 per stage)
-constexpr int TMEM_AHI = 384;                 // first column of the raw A k-blocks (32 per stage, <= 4 stages)
+constexpr int GEMM_SMEM = RING_BYTES + EPI_BYTES + 512 + 1024;  // + barriers + alignment slack
+constexpr int TMEM_COLS = 512;                // 2 x 128 accumulators + NT x 32 columns of split k-blocks
+constexpr int TMEM_SPLIT = 256;               // first column of the split k-block slots
 
 constexpr int WG_TB = 32;                     // tokens per wgrad stage (4 MMAs of K=8)
 constexpr int WG_STAGES = 6;
@@ -103,27 +134,60 @@ __device__ __forceinline__ uint32_t epi_off(int row, int col4 /* col / 4 */) {
   return box * TILE_BYTES + row * 128 + chunk * 16;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+
+// Splitter body (split mode), thread == tile row: the row's 32 fp32 of a k-block -> 32 packed words for its TMEM slot
+//   columns [TMEM_SPLIT + 32 ts, +16):      fp16(a)            } packed pairs (element 2c low half, 2c + 1 high half):
+//   columns [TMEM_SPLIT + 32 ts + 16, +16): fp16(a - fp16(a))  } A operands of the kind::f16 MMAs
+__device__ __forceinline__ void split_row_load(const uint8_t* sa, int row, float* out) {
+  uint32_t* pk = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
+    f16_split2(a.x, a.y, pk[c * 2 + 0], pk[16 + c * 2 + 0]);
+    f16_split2(a.z, a.w, pk[c * 2 + 1], pk[16 + c * 2 + 1]);
+  }
+}
+// The 6 MMAs (kind::f16, K = 16) of a split k-block: D (+)= A_h.B_h + A_h.B_r + A_r.B_h with x = x_h + x_r the two-term
+// FP16 split (f16_split2): fp32-accurate at half the tensor-pipe time of three TF32 products, and on 16-bit weight
+// tiles. sb = shared address of the weight k-block: fp16(B) then fp16(B_r), 8 KB each (128 rows x 64 B, 64B swizzle).
+__device__ __forceinline__ void issue_split_kblock(uint32_t tmem_d, uint32_t tmem_base, int ts, uint32_t sb, bool first) {
+  constexpr uint32_t idesc16 = umma_idesc_f16(BM, BN, 0, 0);
+  const uint64_t dbh = umma_smem_desc(sb, 16, 512, 4);
+  const uint64_t dbr = umma_smem_desc(sb + TILE_BYTES / 2, 16, 512, 4);
+  const uint32_t tah = tmem_base + TMEM_SPLIT + ts * 32;
+  const uint32_t tar = tah + 16;
+  // advance along K inside the 64-byte swizzle span: 16 halves = 32 B -> +2 in the (addr >> 4) field
+#pragma unroll
+  for (int j = 0; j < BK / 16; ++j) {
+    umma_f16_ts(tmem_d, tah + 8 * j, dbh + 2 * j, idesc16, (!first || j > 0) ? 1u : 0u);   // A_h . B_h
+    umma_f16_ts(tmem_d, tah + 8 * j, dbr + 2 * j, idesc16, 1u);                            // A_h . B_r
+    umma_f16_ts(tmem_d, tar + 8 * j, dbh + 2 * j, idesc16, 1u);                            // A_r . B_h
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint8_t* epi = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi = smem + RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
-  uint64_t* full = bars;                 // [MAX_STAGES]
-  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* full = bars;                 // [MAX_STAGES] stage landed (3xTF32: activation slot landed)
+  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES] stage free (3xTF32: activation slot read by the 4 splitter warps)
   uint64_t* tfull = bars + 2 * MAX_STAGES;  // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* auxfull = tempty + 2;        // [1]
-  uint64_t* lofull = auxfull + 1;        // [MAX_STAGES] A_lo of the stage is in TMEM
-  uint64_t* auxbox = lofull + MAX_STAGES;  // [4] streaming epilogue: aux chunk of a staging box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbox + 4);
-  // ring geometry: the HBM latency is hidden by bytes in flight, so the single-pass mode (no B_lo tile) turns the
-  // spare third of each stage into a fourth stage
-  const int nstages = g.split ? STAGES : STAGES_1P;
-  const int stage_bytes = g.split ? STAGE_BYTES : 2 * TILE_BYTES;
+  uint64_t* lofull = auxfull + 1;        // [NT] split k-block is in its TMEM slot
+  uint64_t* auxbox = lofull + NT;        // [4] streaming epilogue: aux chunk of a staging box landed
+  uint64_t* tfree = auxbox + 4;          // [NT] TMEM slot consumed by the MMAs
+  uint64_t* bfull = tfree + NT;          // [NB] weight slot landed
+  uint64_t* bempty = bfull + NB;         // [NB] weight slot consumed by the MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + NB);
+  constexpr int nstages = STAGES_1P;            // single-pass ring
+  constexpr int stage_bytes = 2 * TILE_BYTES;
+  uint8_t* bring = ring + NA * TILE_BYTES;      // 3xTF32: weight slots behind the activation slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,8 +203,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], g.split ? 4 : 1);
+    }
+    for (int s = 0; s < NT; ++s) {
       mbar_init(&lofull[s], 4);
+      mbar_init(&tfree[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -160,11 +231,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int step = gridDim.x;
 
   if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (3xTF32: activation slots only)
     if (lane == 0) {
+      const int ns = g.split ? NA : nstages;
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (g.split ? 3 : 2) * TILE_BYTES;
       for (int item = first; item < g.num_items; item += step) {
         const int n_t = item % g.n_tiles;
         const int rest = item / g.n_tiles;
@@ -176,27 +247,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           GP_T0();
           mbar_wait(&empty[stage], phase ^ 1);
           GP_ADD(0);
-          mbar_expect_tx(&full[stage], tx);
-          uint8_t* sa = ring + stage * stage_bytes;
-#ifdef GEMM_DBG_L2_A   // experiment: every A tile comes from row tile 0 (L2 hit) -- separates HBM latency from on-chip limits
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, 0);
-#else
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
-#endif
-          tma_load_2d(sa + TILE_BYTES, &tmB, &full[stage], kb * BK, n_t * BN);
-          if (g.split) tma_load_2d(sa + 2 * TILE_BYTES, &tmBlo, &full[stage], kb * BK, n_t * BN);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          if (g.split) {
+            mbar_expect_tx(&full[stage], TILE_BYTES);
+            tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, m_t * BM);
+          } else {
+            mbar_expect_tx(&full[stage], 2 * TILE_BYTES);
+            uint8_t* sa = ring + stage * stage_bytes;
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_t * BM);
+            tma_load_2d(sa + TILE_BYTES, &tmB, &full[stage], kb * BK, n_t * BN);
+          }
+          if (++stage == ns) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ TMA producer of the weight slots (3xTF32)
+    // B and B_lo k-blocks come from L2 (every CTA reads the same weight image); their slots are held until the MMAs
+    // that read them retire, so they cycle on their own barriers and never hold an activation slot back.
+    if (lane == 0 && g.split) {
+      int bs = 0;
+      uint32_t bphase = 0;
+      for (int item = first; item < g.num_items; item += step) {
+        const int n_t = item % g.n_tiles;
+        const int ks = (item / g.n_tiles) % g.k_splits;
+        const int kb0 = ks * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.K / BK);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bempty[bs], bphase ^ 1);
+          mbar_expect_tx(&bfull[bs], BSLOT_BYTES);
+          uint8_t* sb = bring + bs * BSLOT_BYTES;
+          tma_load_2d(sb, &tmBlo, &bfull[bs], kb * BK, n_t * BN);                          // fp16(B)
+          tma_load_2d(sb + BSLOT_BYTES / 2, &tmBlo, &bfull[bs], kb * BK, g.N + n_t * BN);  // fp16(B_r)
+          if (++bs == NB) { bs = 0; bphase ^= 1; }
         }
       }
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ A_lo splitters (3xTF32 mode only)
-    // thread == tile row: read its 32 fp32 of the k-block from the swizzled smem tile, keep what the
-    // tensor core's operand truncation drops, park it in TMEM as the A operand of a TS-mode MMA.
+    // thread == tile row: read its 32 fp32 of the k-block from the swizzled smem slot, hand the slot straight back to
+    // the producer (the k-block now lives in registers), then park the raw values and what the tensor core's operand
+    // truncation drops in a TMEM slot as the A operands of the TS-mode MMAs.
     if (g.split) {
       const int row = threadIdx.x;  // 0..127 == TMEM lane
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ts = 0;
+      uint32_t phase = 0, tphase = 0;
       for (int item = first; item < g.num_items; item += step) {
         const int ks = (item / g.n_tiles) % g.k_splits;
         const int kb0 = ks * g.kb_per_split;
@@ -205,33 +299,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           GP_T0();
           mbar_wait(&full[stage], phase);
           if (threadIdx.x == 0) GP_ADD(1);
-          const uint8_t* sa = ring + stage * stage_bytes + row * 128;
-          float lo[32], hi[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
-            hi[c * 4 + 0] = a.x; hi[c * 4 + 1] = a.y; hi[c * 4 + 2] = a.z; hi[c * 4 + 3] = a.w;
-            lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
-            lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
-          }
+          float sp[32];
+          split_row_load(ring + stage * TILE_BYTES + row * 128, row, sp);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);   // slot read by this warp's 32 rows
           if (threadIdx.x == 0) GP_ADD(2);
-          tmem_st_32x32_nowait(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_AHI + stage * BK, hi);
-          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
+          mbar_wait(&tfree[ts], tphase ^ 1);
+          tc_fence_after();
+          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_SPLIT + ts * 32, sp);
           if (threadIdx.x == 0) GP_ADD(3);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (lane == 0) mbar_arrive(&lofull[ts]);
           if (threadIdx.x == 0) GP_ADD(4);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          if (++stage == NA) { stage = 0; phase ^= 1; }
+          if (++ts == NT) { ts = 0; tphase ^= 1; }
         }
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+#ifdef GEMM_CLOCKS
+      const long long gc0 = clock64();
+      unsigned long long gt0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
+      int stage = 0, ts = 0, bs = 0;
+      uint32_t phase = 0, tphase = 0, bphase = 0;
       int it = 0;
       for (int item = first; item < g.num_items; item += step, ++it) {
         const int rest = item / g.n_tiles;
@@ -249,41 +345,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           GP_T0();
-          mbar_wait(&full[stage], phase);
-          GP_ADD(5);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
-          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = umma_smem_desc_sw128(sa + TILE_BYTES, 16, 1024);
-          const uint64_t dbl = umma_smem_desc_sw128(sa + 2 * TILE_BYTES, 16, 1024);
-          const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
           if (g.split) {
-            // 3xTF32: all three products take A from TMEM (raw and low k-block, parked there by the splitter warps).
-            // An SS-mode TF32 MMA reads 4 KB of A and 4 KB of B from shared memory every 64 clocks -- the whole
-            // 128 B/clk of the SM -- so with A in TMEM the twelve MMAs of a k-block read 48 KB instead of 80 KB and
-            // leave room for the TMA writes and the epilogue staging traffic.
-            mbar_wait(&lofull[stage], phase);
+            // 3xTF32-accurate product: all MMAs take A from TMEM (parked there by the splitter warps), see
+            // issue_split_kblock
+            mbar_wait(&bfull[bs], bphase);
+            GP_ADD(5);
+            mbar_wait(&lofull[ts], tphase);
             GP_ADD(6);
             tc_fence_after();
-            const uint32_t tahi = tmem_base + TMEM_AHI + stage * BK;
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              // advance 8 fp32 (32 B) along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-              umma_tf32_ts(tmem_d, tahi + 8 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);  // trunc(A) . trunc(B)
-              umma_tf32_ts(tmem_d, tahi + 8 * k, dbl + 2 * k, idesc, 1u);                            // trunc(A) . B_lo
-              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);                             // A_lo . trunc(B)
+            if (elect_one()) {
+              issue_split_kblock(tmem_d, tmem_base, ts, smem_u32(bring + bs * BSLOT_BYTES), kb == kb0);
+              umma_commit(&bempty[bs]);  // weight slot and TMEM slot are free when these MMAs are done
+              umma_commit(&tfree[ts]);
             }
+            __syncwarp();
+            if (++bs == NB) { bs = 0; bphase ^= 1; }
+            if (++ts == NT) { ts = 0; tphase ^= 1; }
           } else {
+            mbar_wait(&full[stage], phase);
+            GP_ADD(5);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+            const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(sa + TILE_BYTES, 16, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 8; ++k)
+                umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);  // frees the smem stage (and its A_lo columns) when these MMAs are done
           GP_ADD(7);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);      // accumulator complete
+        if (elect_one()) umma_commit(&tfull[acc]);      // accumulator complete
+        __syncwarp();
       }
+#ifdef GEMM_CLOCKS
+      if (blockIdx.x == 0 && lane == 0) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        gemm_clk[0] = clock64() - gc0;
+        gemm_clk[1] = (long long)(gt1 - gt0);
+      }
+#endif
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
@@ -502,14 +608,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <bool SPLIT, int MASK = 0>
 struct Bres {
   static constexpr int NKB = 4;                                  // K = 128 = 4 k-blocks of 32
-  static constexpr int B_KB_BYTES = (SPLIT ? 2 : 1) * TILE_BYTES; // hi (+ lo) of one k-block
-  static constexpr int B_BYTES = NKB * B_KB_BYTES;               // 64 KB / 128 KB
-  static constexpr int ASTAGES = SPLIT ? 4 : (MASK == 2 ? 5 : 6); // 16 KB activation k-blocks in flight
-  static constexpr int EPI_COLS = SPLIT ? 64 : 128;              // staging tile: half / full width
+  static constexpr int B_KB_BYTES = TILE_BYTES;                  // fp32 k-block, or its fp16 B_h + B_r tiles (2 x 8 KB)
+  static constexpr int B_BYTES = NKB * B_KB_BYTES;               // 64 KB
+  static constexpr int ASTAGES = SPLIT ? BRES_SPLIT_ASTAGES : (MASK == 2 ? 5 : 6);  // 16 KB activation k-blocks in flight
+  static constexpr int EPI_COLS = SPLIT ? BRES_SPLIT_EPI_COLS : 128;  // staging tile: boxes of 32 columns
   static constexpr int EPI_B = BM * EPI_COLS * 4;
   static constexpr int GATE_BOX = BM * 16;                       // MASK == 2: 4 gate words per row of a tile
   static constexpr int GATE_B = MASK == 2 ? 4 * GATE_BOX : 0;    // ring of 4 tiles
-  static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + GATE_B + 256 + 1024;
+  static constexpr int SMEM = B_BYTES + ASTAGES * TILE_BYTES + EPI_B + GATE_B + 512 + 1024;
 };
 
 // MASK: 0 none | 1 the relu epilogue also writes the sign of its output as a bit image | 2 the output is gated by a
@@ -534,12 +640,13 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbox + C::GATE_B);
   uint64_t* full = bars;                        // [ASTAGES]
   uint64_t* empty = full + C::ASTAGES;          // [ASTAGES]
-  uint64_t* lofull = empty + C::ASTAGES;        // [ASTAGES]
-  uint64_t* tfull = lofull + C::ASTAGES;        // [2]
+  uint64_t* lofull = empty + C::ASTAGES;        // [NT] split k-block is in its TMEM slot
+  uint64_t* tfull = lofull + NT;                // [2]
   uint64_t* tempty = tfull + 2;                 // [2]
   uint64_t* auxfull = tempty + 2;               // [4] one per staging box (aux chunk landed)
   uint64_t* bfull = auxfull + 4;                // [1] weights resident
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* tfree = bfull + 1;                  // [NT] 3xTF32: TMEM slot of a split k-block consumed by the MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfree + NT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -554,8 +661,11 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < C::ASTAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], SPLIT ? 4 : 1);   // split mode: the four splitter warps free the slot, else the MMA commit
+    }
+    for (int s = 0; s < NT; ++s) {
       mbar_init(&lofull[s], 4);
+      mbar_init(&tfree[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -571,6 +681,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // activation slots in use. Measured (1.55 M rows, split mode): with ONE column tile (every CTA streams its own rows) four
+  // slots beat six by 10 % (258 vs 284 us); with three or four column tiles sharing each row tile six beat four by 4 %.
+  const int nst = (SPLIT && g.n_tiles == 1) ? 4 : C::ASTAGES;
   // this CTA: column tile n_t, row tiles m0, m0 + groups, ...
   const int n_t = blockIdx.x % g.n_tiles;
   const int groups = gridDim.x / g.n_tiles;
@@ -581,8 +694,12 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(bfull, C::B_BYTES);
       for (int kb = 0; kb < C::NKB; ++kb) {
-        tma_load_2d(bsm + kb * C::B_KB_BYTES, &tmB, bfull, kb * BK, n_t * BN);
-        if (SPLIT) tma_load_2d(bsm + kb * C::B_KB_BYTES + TILE_BYTES, &tmBlo, bfull, kb * BK, n_t * BN);
+        if (SPLIT) {   // fp16 B_h and B_r tiles (see issue_split_kblock)
+          tma_load_2d(bsm + kb * C::B_KB_BYTES, &tmBlo, bfull, kb * BK, n_t * BN);
+          tma_load_2d(bsm + kb * C::B_KB_BYTES + TILE_BYTES / 2, &tmBlo, bfull, kb * BK, g.N + n_t * BN);
+        } else {
+          tma_load_2d(bsm + kb * C::B_KB_BYTES, &tmB, bfull, kb * BK, n_t * BN);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -593,7 +710,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           GP_ADD(0);
           mbar_expect_tx(&full[stage], TILE_BYTES);
 #ifdef GEMM_PROFILE
-          if (phase || m_t != m0) { gp_acc[15] += clock64() - gp_commit_t[stage]; }
+          if (!SPLIT && (phase || m_t != m0)) { gp_acc[15] += clock64() - gp_commit_t[stage]; }
           gp_issue_t[stage] = clock64();
 #endif
 #ifdef GEMM_DBG_L2_A
@@ -601,15 +718,15 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #else
           tma_load_2d(ring + stage * TILE_BYTES, &tmA, &full[stage], kb * BK, m_t * BM);
 #endif
-          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp < 4) {
     if (SPLIT) {
       const int row = threadIdx.x;
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ts = 0;
+      uint32_t phase = 0, tphase = 0;
       for (int m_t = m0; m_t < m_tiles; m_t += groups) {
         for (int kb = 0; kb < C::NKB; ++kb) {
           GP_T0();
@@ -618,29 +735,24 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef GEMM_PROFILE
           if (threadIdx.x == 0) { gp_acc[13] += clock64() - gp_issue_t[stage]; gp_acc[14] += 1; }
 #endif
-#ifndef GEMM_DBG_NOST
-          const uint8_t* sa = ring + stage * TILE_BYTES + row * 128;
-          float lo[32], hi[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 a = *reinterpret_cast<const float4*>(sa + ((c ^ (row & 7)) << 4));
-            hi[c * 4 + 0] = a.x; hi[c * 4 + 1] = a.y; hi[c * 4 + 2] = a.z; hi[c * 4 + 3] = a.w;
-            lo[c * 4 + 0] = tf32_lo(a.x); lo[c * 4 + 1] = tf32_lo(a.y);
-            lo[c * 4 + 2] = tf32_lo(a.z); lo[c * 4 + 3] = tf32_lo(a.w);
-          }
-          tmem_st_32x32_nowait(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_AHI + stage * BK, hi);
-          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_ALO + stage * BK, lo);
-#endif
+          float sp[32];
+          split_row_load(ring + stage * TILE_BYTES + row * 128, row, sp);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);   // the k-block is in registers: the slot goes back to the producer
+          mbar_wait(&tfree[ts], tphase ^ 1);
+          tc_fence_after();
+          tmem_st_32x32(tmem_base + (uint32_t(warp * 32) << 16) + TMEM_SPLIT + ts * 32, sp);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&lofull[stage]);
+          if (lane == 0) mbar_arrive(&lofull[ts]);
           if (threadIdx.x == 0) GP_ADD(2);
-          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (++ts == NT) { ts = 0; tphase ^= 1; }
         }
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues (see elect_one)
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
       mbar_wait(bfull, 0);
 #ifdef GEMM_CLOCKS
@@ -648,8 +760,8 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       unsigned long long gt0;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #endif
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ts = 0;
+      uint32_t phase = 0, tphase = 0;
       int it = 0;
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
@@ -663,40 +775,41 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < C::NKB; ++kb) {
           GP_T0();
-#ifdef GEMM_PROFILE
-          gp_acc[12] += clock64() - gp_issue_t[stage];   // age of this stage's TMA when the issuer gets to it
-#endif
-          mbar_wait(&full[stage], phase);
-          GP_ADD(5);
-          tc_fence_after();
-          const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + stage * TILE_BYTES), 16, 1024);
-          const uint64_t db = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES), 16, 1024);
-          const uint64_t dbl = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES + TILE_BYTES), 16, 1024);
-          const uint32_t talo = tmem_base + TMEM_ALO + stage * BK;
-          if (SPLIT) {   // all three products with A from TMEM (see gemm_tc_kernel)
-            mbar_wait(&lofull[stage], phase);
+          if (SPLIT) {   // all products with A from TMEM (see issue_split_kblock); the activation slot is already free
+            mbar_wait(&lofull[ts], tphase);
             GP_ADD(6);
             tc_fence_after();
-            const uint32_t tahi = tmem_base + TMEM_AHI + stage * BK;
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              umma_tf32_ts(tmem_d, tahi + 8 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(tmem_d, tahi + 8 * k, dbl + 2 * k, idesc, 1u);
-              umma_tf32_ts(tmem_d, talo + 8 * k, db + 2 * k, idesc, 1u);
+            if (elect_one()) {
+              issue_split_kblock(tmem_d, tmem_base, ts, smem_u32(bsm + kb * C::B_KB_BYTES), kb == 0);
+              umma_commit(&tfree[ts]);
             }
+            __syncwarp();
+            if (++ts == NT) { ts = 0; tphase ^= 1; }
           } else {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);
 #ifdef GEMM_PROFILE
-          gp_commit_t[stage] = clock64();
+            gp_acc[12] += clock64() - gp_issue_t[stage];   // age of this stage's TMA when the issuer gets to it
 #endif
+            mbar_wait(&full[stage], phase);
+            GP_ADD(5);
+            tc_fence_after();
+            const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + stage * TILE_BYTES), 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(smem_u32(bsm + kb * C::B_KB_BYTES), 16, 1024);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 8; ++k)
+                umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+#ifdef GEMM_PROFILE
+            gp_commit_t[stage] = clock64();
+#endif
+            if (++stage == nst) { stage = 0; phase ^= 1; }
+          }
           GP_ADD(7);
-          if (++stage == C::ASTAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
       }
 #ifdef GEMM_CLOCKS
       if (blockIdx.x == 0) {
@@ -1130,6 +1243,59 @@ static int get_tmap(TmapCache* tc, const float* ptr, int rows, int cols, int ld,
   return TPC_OK;
 }
 
+// split image of a forward weight: [2 N][K] fp16 (plane 0 = B_h = fp16(B), plane 1 = B_r = fp16(B - B_h)), ld elements
+// per row; boxes of 128 rows x 32 columns (64 B) in the 64-byte swizzle
+static int get_tmap_corr(TmapCache* tc, const void* ptr, int rows2, int cols, int ld, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows2, cols, ld, BN, 2);
+  std::lock_guard<std::mutex> lk(tc->mu);
+  auto it = tc->maps.find(key);
+  if (it != tc->maps.end()) {
+    *out = it->second;
+    return TPC_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0) {
+    fprintf(stderr, "[tpc] tensor map: correction image pointer/ld not 16-byte aligned (ptr=%p ld=%d)\n", ptr, ld);
+    return TPC_ERR_ARG;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[tpc] cuTensorMapEncodeTiled (correction image) failed: %d (rows=%d cols=%d ld=%d)\n", (int)r, rows2,
+            cols, ld);
+    return TPC_ERR_DRIVER;
+  }
+  if (tc->maps.size() > 4096) tc->maps.clear();
+  tc->maps[key] = m;
+  *out = m;
+  return TPC_OK;
+}
+
+__global__ void split_image_kernel(const float* __restrict__ Bt, int ldb, int N, int K, __half* __restrict__ img) {
+  const long long n = (long long)N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K), c = (int)(i % K);
+    const float v = Bt[(size_t)r * ldb + c];
+    const __half hv = f16_hi(v);
+    img[(size_t)r * ldb + c] = hv;
+    img[((size_t)N + r) * ldb + c] = f16_hi(v - __half2float(hv));
+  }
+}
+
+int build_split_image(const float* Bt, int ldb, int N, int K, void* image, cudaStream_t stream) {
+  if (!Bt || !image || N <= 0 || K <= 0 || ldb < K) return TPC_ERR_ARG;
+  const long long n = (long long)N * K;
+  const int grid = (int)std::min<long long>((n + 255) / 256, 1184);
+  split_image_kernel<<<grid, 256, 0, stream>>>(Bt, ldb, N, K, static_cast<__half*>(image));
+  TPC_CHECK_LAUNCH();
+  return TPC_OK;
+}
+
 bool gemm_weight_resident(int M, int N, int K, const GemmEpi& epi, bool split, int num_sms) {
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
   return (K == 128) && N % BN == 0 && !epi.ln && !epi.atomic && !(split && epi.aux_mode) && n_tiles <= num_sms &&
@@ -1137,7 +1303,7 @@ bool gemm_weight_resident(int M, int N, int K, const GemmEpi& epi, bool split, i
 }
 
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
-                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const float* Bt_lo) {
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const void* Bt_lo) {
   TPC_TRY(gemm_tc_init());
   if (M <= 0) return TPC_OK;
   if (N % BN != 0 || K % BK != 0 || K <= 0) return TPC_ERR_SHAPE;
@@ -1160,7 +1326,7 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   CUtensorMap tA, tB, tBlo, tAux, tD;
   TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
   TPC_TRY(get_tmap(tc, Bt, N, K, ldb, BN, 0, &tB));
-  if (Bt_lo) { TPC_TRY(get_tmap(tc, Bt_lo, N, K, ldb, BN, 0, &tBlo)); } else { tBlo = tB; }
+  if (Bt_lo) { TPC_TRY(get_tmap_corr(tc, Bt_lo, 2 * N, K, ldb, &tBlo)); } else { tBlo = tB; }
   TPC_TRY(get_tmap(tc, D, M, N, ldd, BM, 0, &tD));
   if (epi.aux_mode) {
     if (!epi.aux) return TPC_ERR_ARG;
@@ -1187,7 +1353,7 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     return TPC_OK;
   }
   const int grid = g.num_items < num_sms ? g.num_items : num_sms;
-  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+  gemm_tc_kernel<<<grid, GEMM_TC_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

@@ -39,11 +39,15 @@ void tmap_cache_destroy(TmapCache*);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes. idempotent.
 
 // D[M,N] = epi(A[M,K] @ Bt[N,K]^T). K % 32 == 0, N % 128 == 0. k_splits > 1 requires epi.atomic.
-// Bt_lo != nullptr selects 3xTF32: Bt holds the raw fp32 weights (the tensor core truncates them), Bt_lo what the
-// truncation drops; the A-side low part is split on chip. Result is fp32-accurate (~2^-21 relative).
+// Bt_corr != nullptr selects the fp32-accurate split product ("3xTF32" with cheaper correction terms):
+//   D = trunc(A).trunc(B) [TF32] + bf16(A).bf16(B_lo) + bf16(A_lo).bf16(B) [kind::f16], x_lo = x - trunc_tf32(x).
+// Bt holds the raw fp32 weights (the tensor core truncates them), Bt_corr the bf16 correction image
+// [2][N][ldb] = {bf16(B), bf16(B_lo)} made by build_split_image (same byte size as an fp32 [N][ldb] matrix); the
+// A-side parts are split on chip. Error ~2^-19 relative (bf16 keeps 8 bits of terms that are 2^-11 of the product).
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
                 int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream,
-                const float* Bt_lo = nullptr);
+                const void* Bt_corr = nullptr);
+int build_split_image(const float* Bt, int ldb, int N, int K, void* image, cudaStream_t stream);
 
 // dW[nj][Kin, 128] += X[M,Kin]^T @ dY[M, nj*128 .. nj*128+127]  for every 128-wide column tile nj of dY.
 // dptr[nj] is the destination of tile nj with leading dimension ldd[nj]; accumulation is atomic.

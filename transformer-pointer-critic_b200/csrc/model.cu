@@ -38,12 +38,12 @@ struct Builder {
     soff += (n + 255) & ~size_t(255);  // 1 KB alignment keeps every TMA base 16-byte aligned
     return o;
   }
-  // transposed RAW copy of W[in][out] into dst[out][in] (ld = ld_dst) at row offset row0: forward B operand of the
-  // 3xTF32 GEMM (the tensor core truncates it); the matching low part goes to the mirror half of the image
-  // (patched to dst + shadow_half once the layout is complete: round == 2)
-  void job_t(const DenseP& d, size_t dst, int ld_dst, int row0) {
+  // transposed RAW copy of W[in][out] into dst[out][in] (ld = ld_dst) at row offset row0 of a matrix with mat_rows
+  // rows: forward B operand of the split GEMM (the tensor core truncates it); the matching bf16 correction image goes to
+  // the mirror half of the shadow buffer (patched to dst + shadow_half once the layout is complete: round == 2)
+  void job_t(const DenseP& d, size_t dst, int ld_dst, int row0, int mat_rows = 0) {
     jobs->push_back({d.w, dst + (size_t)row0 * ld_dst, d.out, d.in, ld_dst, d.out, 1, 0});
-    jobs->push_back({d.w, dst + (size_t)row0 * ld_dst, d.out, d.in, ld_dst, d.out, 1, 2});
+    jobs->push_back({d.w, dst, d.out, d.in, ld_dst, d.out, 1, 2, row0, mat_rows ? mat_rows : d.out});
   }
   // rounded copy of W[in][out] into dst[in][ld_dst] at column offset col0
   void job_c(const DenseP& d, size_t dst, int ld_dst, int col0) {
@@ -71,7 +71,7 @@ struct Builder {
     e.s.wqkv_c = salloc(3 * D_MODEL * D_MODEL);
     const DenseP* qkv[3] = {&e.mha.q, &e.mha.k, &e.mha.v};
     for (int j = 0; j < 3; ++j) {
-      job_t(*qkv[j], e.s.wqkv_t, D_MODEL, j * D_MODEL);
+      job_t(*qkv[j], e.s.wqkv_t, D_MODEL, j * D_MODEL, 3 * D_MODEL);
       job_c(*qkv[j], e.s.wqkv_c, 3 * D_MODEL, j * D_MODEL);
       job_bias(*qkv[j], e.s.bqkv, j * D_MODEL);
     }
@@ -89,8 +89,14 @@ __global__ void shadow_kernel(const float* __restrict__ params, float* __restric
   for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x) {
     const int r = (int)(i / j.cols), c = (int)(i % j.cols);
     float v = j.transpose ? params[j.src + (size_t)c * j.ld_src + r] : params[j.src + (size_t)r * j.ld_src + c];
+    if (j.round == 2) {
+      __half* img = reinterpret_cast<__half*>(shadow + j.dst);
+      const __half hv = f16_hi(v);
+      img[(size_t)(j.row0 + r) * j.ld_dst + c] = hv;
+      img[(size_t)(j.mat_rows + j.row0 + r) * j.ld_dst + c] = f16_hi(v - __half2float(hv));
+      continue;
+    }
     if (j.round == 1) v = tf32_rn(v);
-    else if (j.round == 2) v = tf32_lo(v);
     shadow[j.dst + (size_t)r * j.ld_dst + c] = v;
   }
 }
@@ -186,7 +192,7 @@ int build_layout(const ModelDims& md, bool actor, NetLayout* L, std::vector<Shad
       const bool last = (i == L->nl - 1);
       const DenseP* kvp[3] = {&d.mha2.k, &d.mha2.v, &L->W2};
       for (int j = 0; j < (last ? 3 : 2); ++j) {
-        b.job_t(*kvp[j], d.s.wkvp_t, D_MODEL, j * D_MODEL);
+        b.job_t(*kvp[j], d.s.wkvp_t, D_MODEL, j * D_MODEL, 3 * D_MODEL);
         b.job_c(*kvp[j], d.s.wkvp_c, 3 * D_MODEL, j * D_MODEL);
         b.job_bias(*kvp[j], d.s.bkvp, j * D_MODEL);
       }
@@ -202,7 +208,7 @@ int build_layout(const ModelDims& md, bool actor, NetLayout* L, std::vector<Shad
   }
   L->total = b.off;
   L->shadow_half = b.soff;
-  L->shadow_total = 2 * b.soff;   // [main image | low parts of the forward weights at the same offsets]
+  L->shadow_total = 2 * b.soff;   // [main image | bf16 correction images of the forward weights at the same offsets]
   for (ShadowJob& j : *jobs)
     if (j.round == 2) j.dst += L->shadow_half;
   return TPC_OK;

@@ -59,7 +59,7 @@ struct NetLayout {
   int S_critic = 0;
   size_t total = 0;         // canonical parameter count
   size_t shadow_total = 0;  // floats in the shadow buffer
-  size_t shadow_half = 0;   // forward weight W_t at offset o has its 3xTF32 low part at o + shadow_half
+  size_t shadow_half = 0;   // forward weight W_t at offset o has its fp16 split image at o + shadow_half
   std::vector<TensorInfo> tensors;  // canonical tensors in order (Adam / clipnorm granularity)
 };
 
@@ -70,7 +70,10 @@ struct ShadowJob {
   int ld_dst;                    // leading dimension of destination
   int ld_src;                    // leading dimension of source
   int transpose;                 // 1: dst[r][c] = src[c][r] ; 0: dst[r][c] = src[r][c]
-  int round;                     // 0 raw copy | 1 RN-round to TF32 | 2 low part x - trunc_tf32(x)
+  int round;                     // 0 raw copy | 1 RN-round to TF32 | 2 fp16 split image (see below)
+  // round == 2: dst is the float offset of the whole [mat_rows][ld_dst] matrix in the mirror half of the image, read
+  // as fp16 [2][mat_rows][ld_dst]: plane 0 = x_h = fp16(x), plane 1 = fp16(x - x_h); this block starts at row0
+  int row0 = 0, mat_rows = 0;
 };
 
 struct ModelDims {

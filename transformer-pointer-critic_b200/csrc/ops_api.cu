@@ -145,11 +145,11 @@ int tpc_destroy(tpc_handle* h) {
 int tpc_num_sms(const tpc_handle* h) { return h ? h->num_sms : 0; }
 
 // D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags: bit0 relu, bit1 layernorm(+rstd), bit2 round_out,
-// bit3 atomic split-K; aux_mode 0/1/2 (none / add / relu-gate). Bt_lo != NULL: 3xTF32 (Bt raw fp32, Bt_lo = Bt -
-// trunc_tf32(Bt)), fp32-accurate result.
+// bit3 atomic split-K; aux_mode 0/1/2 (none / add / relu-gate). Bt_corr != NULL: fp32-accurate split product (Bt raw
+// fp32, Bt_corr = the bf16 correction image of tpc_gemm_split_image).
 int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
              const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
-             float* rstd_out, int flags, int k_splits, const float* Bt_lo, void* stream) {
+             float* rstd_out, int flags, int k_splits, const void* Bt_corr, void* stream) {
   if (!h) return TPC_ERR_ARG;
   GemmEpi e;
   e.bias = bias;
@@ -163,7 +163,12 @@ int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, f
   e.ln = (flags & 2) ? 1 : 0;
   e.round_out = (flags & 4) ? 1 : 0;
   e.atomic = (flags & 8) ? 1 : 0;
-  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream, Bt_lo);
+  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream, Bt_corr);
+}
+
+int tpc_gemm_split_image(tpc_handle* h, const float* Bt, int ldb, int N, int K, void* image, void* stream) {
+  if (!h) return TPC_ERR_ARG;
+  return build_split_image(Bt, ldb, N, K, image, (cudaStream_t)stream);
 }
 
 // dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout]   (dW row-major with leading dimension ldw, atomically accumulated);
