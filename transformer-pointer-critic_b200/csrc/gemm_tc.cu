@@ -44,7 +44,7 @@ constexpr int BK = 32;                        // fp32 columns per k-block == one
 //                the MMAs) + NB weight slots (fp16 B_h + B_r, 16 KB, served by L2; freed by the MMA commit)
 //   single-pass: 5 stages of A + B (32 KB), freed by the MMA commit (SS-mode MMAs read A from shared memory)
 #ifndef GEMM_NA
-#define GEMM_NA 6
+#define GEMM_NA 5
 #endif
 #ifndef GEMM_NB
 #define GEMM_NB 4
@@ -61,11 +61,14 @@ constexpr int NT = 8;                         // TMEM slots of a split k-block (
 constexpr int STAGES_1P = 5;
 constexpr int MAX_STAGES = 6;
 constexpr int RING_BYTES = 160 * 1024;
+constexpr int LN_SCRATCH_OFF = (NA + NB) * 16 * 1024;   // split mode leaves the tail of the ring free: LayerNorm row partials
+static_assert(LN_SCRATCH_OFF + 2048 <= RING_BYTES && (STAGES_1P - 1) * 32 * 1024 <= LN_SCRATCH_OFF, "LayerNorm scratch must not overlap a live stage");
 constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
 constexpr int BSLOT_BYTES = TILE_BYTES;       // split mode: fp16 B_h + B_r tiles of a k-block (2 x 8 KB)
 constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
 constexpr int GEMM_THREADS = 320;             // warps 0-3 A_lo splitters, 4-7 epilogue, 8 TMA, 9 MMA
-constexpr int GEMM_TC_THREADS = 352;          // generic kernel: + warp 10 = TMA producer of the weight slots (3xTF32)
+constexpr int GEMM_TC_THREADS = 480;          // generic kernel: + warp 10 = TMA producer of the weight slots (split mode),
+                                              // warps 11-14 = second half of the LayerNorm epilogue
 constexpr int WG_THREADS = 256;
 constexpr int GEMM_SMEM = RING_BYTES + EPI_BYTES + 512 + 1024;  // + barriers + alignment slack
 constexpr int TMEM_COLS = 512;                // 2 x 128 accumulators + NT x 32 columns of split k-blocks
@@ -185,7 +188,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bfull = tfree + NT;          // [NB] weight slot landed
   uint64_t* bempty = bfull + NB;         // [NB] weight slot consumed by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + NB);
-  constexpr int nstages = STAGES_1P;            // single-pass ring
+  // single-pass ring (one stage fewer under a LayerNorm epilogue: its row partials live in the tail of the ring)
+  const int nstages = g.ln ? STAGES_1P - 1 : STAGES_1P;
   constexpr int stage_bytes = 2 * TILE_BYTES;
   uint8_t* bring = ring + NA * TILE_BYTES;      // 3xTF32: weight slots behind the activation slots
 
@@ -215,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], g.ln ? 8 : 4);   // one arrival per epilogue warp (LayerNorm: two warpgroups)
     }
     mbar_init(auxfull, 1);
     for (int a = 0; a < 4; ++a) mbar_init(&auxbox[a], 1);
@@ -391,6 +395,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #endif
     }
+  } else if (g.ln && ((warp >= 4 && warp < 8) || warp >= 11)) {
+    // ------------------------------------------------------------------ LayerNorm epilogue (256 threads)
+    // Two warpgroups share a tile: thread (row, half) owns 64 columns of accumulator row `et` (TMEM lane quarter
+    // warp % 4 either way), so a row lives in 64 registers instead of 128 -- the one-thread-per-row version could not
+    // keep its loads in flight (168 registers, spills) and its 9.6 k clocks per tile bound the K = 128 launches.
+    // Row sums / sums of squared deviations are exchanged through two floats per row in the free tail of the ring.
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = warp >= 11 ? 1 : 0;
+    const int et = q * 32 + lane;              // accumulator row inside the tile == TMEM lane
+    const bool leader = (warp == 4 && lane == 0);
+    float* red_sum = reinterpret_cast<float*>(ring + LN_SCRATCH_OFF);   // [2][128]
+    float* red_ssq = red_sum + 256;                                      // [2][128]
+    uint32_t aux_phase = 0;
+    int it = 0;
+    if (g.aux_mode && leader && first < g.num_items) {
+      const int n_t = first % g.n_tiles;
+      const int m_t = (first / g.n_tiles) / g.k_splits;
+      mbar_expect_tx(auxfull, EPI_BYTES);
+      for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, n_t * BN + j * BK, m_t * BM);
+    }
+    for (int item = first; item < g.num_items; item += step, ++it) {
+      const int n_t = item % g.n_tiles;
+      const int m_t = (item / g.n_tiles) / g.k_splits;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m_t * BM + et;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (g.aux_mode) {
+        mbar_wait(auxfull, aux_phase);
+        aux_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * 64;
+      float v[64];
+      tmem_ld_32x32(taddr, v);
+      tmem_ld_32x32(taddr + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator drained: MMA may start the next-but-one tile
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.aux_mode == 1) a = *reinterpret_cast<const float4*>(epi + epi_off(et, half * 16 + c4));
+        const float4 b = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias) + half * 16 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c4 * 4 + 0] += a.x + b.x;
+        v[c4 * 4 + 1] += a.y + b.y;
+        v[c4 * 4 + 2] += a.z + b.z;
+        v[c4 * 4 + 3] += a.w + b.w;
+        s0 += v[c4 * 4 + 0] + v[c4 * 4 + 1];
+        s1 += v[c4 * 4 + 2] + v[c4 * 4 + 3];
+      }
+      const float my_sum = s0 + s1;
+      red_sum[half * 128 + et] = my_sum;
+      named_bar_sync(2, 256);
+      // both halves add the two partials in the same order: identical mean in both threads of a row
+      const float mean = (red_sum[et] + red_sum[128 + et]) * (1.0f / 128.0f);
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float d0 = v[j] - mean, d1 = v[j + 1] - mean, d2 = v[j + 2] - mean, d3 = v[j + 3] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+      }
+      red_ssq[half * 128 + et] = (q0 + q1) + (q2 + q3);
+      named_bar_sync(2, 256);
+      const float rstd = 1.0f / sqrtf((red_ssq[et] + red_ssq[128 + et]) * (1.0f / 128.0f) + g.ln_eps);
+      if (half == 0 && g.rstd_out && row < g.M) g.rstd_out[row] = rstd;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(g.gamma) + half * 16 + c4);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(g.beta) + half * 16 + c4);
+        float4 o;
+        o.x = (v[c4 * 4 + 0] - mean) * rstd * gm.x + bt.x;
+        o.y = (v[c4 * 4 + 1] - mean) * rstd * gm.y + bt.y;
+        o.z = (v[c4 * 4 + 2] - mean) * rstd * gm.z + bt.z;
+        o.w = (v[c4 * 4 + 3] - mean) * rstd * gm.w + bt.w;
+        if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+        *reinterpret_cast<float4*>(epi + epi_off(et, half * 16 + c4)) = o;
+      }
+      // staging tile complete -> TMA store (rows beyond M are clipped by the tensor map)
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (leader) {
+        for (int j = 0; j < 4; ++j) tma_store_2d(&tmD, epi + j * TILE_BYTES, n_t * BN + j * BK, m_t * BM);
+        tma_store_commit();
+        tma_store_wait_read0();  // staging tile may be overwritten
+        const int next = item + step;
+        if (g.aux_mode && next < g.num_items) {
+          const int nn = next % g.n_tiles;
+          const int nm = (next / g.n_tiles) / g.k_splits;
+          mbar_expect_tx(auxfull, EPI_BYTES);
+          for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, nn * BN + j * BK, nm * BM);
+        }
+      }
+      named_bar_sync(1, 256);
+    }
+    if (leader) tma_store_wait_all0();
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int et = threadIdx.x - 128;          // 0..127 == accumulator row inside the tile == TMEM lane
@@ -501,48 +602,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
 
-      if (g.ln) {
-        // whole row (N == 128) in registers: bias + residual, two-pass mean / variance, scale + shift
-        float v[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + c * 32, v + c * 32);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator drained: MMA may start the next-but-one tile
-        float sum = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.aux_mode == 1) a = *reinterpret_cast<const float4*>(epi + epi_off(et, c4));
-          const float4 b = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[c4 * 4 + 0] += a.x + b.x;
-          v[c4 * 4 + 1] += a.y + b.y;
-          v[c4 * 4 + 2] += a.z + b.z;
-          v[c4 * 4 + 3] += a.w + b.w;
-          sum += (v[c4 * 4 + 0] + v[c4 * 4 + 1]) + (v[c4 * 4 + 2] + v[c4 * 4 + 3]);
-        }
-        const float mean = sum * (1.0f / 128.0f);
-        float ssq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 128; ++j) {
-          const float d = v[j] - mean;
-          ssq = fmaf(d, d, ssq);
-        }
-        const float rstd = 1.0f / sqrtf(ssq * (1.0f / 128.0f) + g.ln_eps);
-        if (g.rstd_out && row < g.M) g.rstd_out[row] = rstd;
-#pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) {
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(g.gamma) + c4);
-          const float4 bt = __ldg(reinterpret_cast<const float4*>(g.beta) + c4);
-          float4 o;
-          o.x = (v[c4 * 4 + 0] - mean) * rstd * gm.x + bt.x;
-          o.y = (v[c4 * 4 + 1] - mean) * rstd * gm.y + bt.y;
-          o.z = (v[c4 * 4 + 2] - mean) * rstd * gm.z + bt.z;
-          o.w = (v[c4 * 4 + 3] - mean) * rstd * gm.w + bt.w;
-          if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
-          *reinterpret_cast<float4*>(epi + epi_off(et, c4)) = o;
-        }
-      } else {
+      {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float v[32];
