@@ -67,6 +67,7 @@ constexpr int TILE_BYTES = BM * BK * 4;       // 16 KB: one operand k-block
 constexpr int BSLOT_BYTES = TILE_BYTES;       // split mode: fp16 B_h + B_r tiles of a k-block (2 x 8 KB)
 constexpr int EPI_BYTES = BM * BN * 4;        // 64 KB staging tile (4 boxes of 128 rows x 32 cols)
 constexpr int GEMM_THREADS = 320;             // warps 0-3 A_lo splitters, 4-7 epilogue, 8 TMA, 9 MMA
+constexpr int BRES_THREADS = 448;             // weight-resident kernel: + warps 10-13 = second epilogue warpgroup
 constexpr int GEMM_TC_THREADS = 480;          // generic kernel: + warp 10 = TMA producer of the weight slots (split mode),
                                               // warps 11-14 = second half of the LayerNorm epilogue
 constexpr int WG_THREADS = 256;
@@ -682,7 +683,7 @@ struct Bres {
 // bit image (ReLU backward). Compile-time so that the plain epilogue -- a latency-critical per-chunk chain -- stays as
 // it is.
 template <bool SPLIT, int MASK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(BRES_THREADS, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
@@ -729,7 +730,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], g.aux_mode == 0 ? 8 : 4);   // one arrival per epilogue warp (no aux input: two warpgroups)
     }
     for (int a = 0; a < 4; ++a) mbar_init(&auxfull[a], 1);
     mbar_init(bfull, 1);
@@ -880,19 +881,25 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 #endif
     }
-  } else if (warp >= 4 && warp < 8) {
-    const int et = threadIdx.x - 128;
+  } else if (g.aux_mode == 0 && ((warp >= 4 && warp < 8) || warp >= 10)) {
+    // Streaming epilogue on two warpgroups: group 0 (warps 4-7) takes the 32-column chunks 0 and 1 of a tile, group 1
+    // (warps 10-13) chunks 2 and 3; a thread owns accumulator row `et` (TMEM lane quarter warp % 4 in both groups).
+    // Every chunk goes through a 16 KB staging box and is stored by TMA right away; each group has its own pair of
+    // boxes, its own named barrier and its own store-issuing leader, so the two chains (TMEM load -> math -> staging ->
+    // store), which were the critical path of this kernel on one warpgroup, run side by side.
+    const int grp = warp >= 10 ? 1 : 0;
     const int q = warp & 3;
-    const bool leader = (et == 0);
+    const int et = q * 32 + lane;
+    const bool leader = lane == 0 && q == 0;
+    const int bar_id = 1 + grp;
     int it = 0;
-    if (g.aux_mode == 0) {
-      // Streaming epilogue: every 32-column chunk goes through its own 16 KB staging box and is stored by TMA
-      // right away; boxes form a ring of NBUF, so the store of chunk c overlaps the TMEM load / math of chunk c+1.
-      constexpr int NBUF = C::EPI_B / TILE_BYTES;       // 2 (3xTF32) or 4
-      int cidx = 0;
+    {
+      int k = 0;   // chunks this group has staged
       // MASK == 2: the gate words of (this column tile, 128 rows) are 2 KB contiguous in global memory (image layout
-      // [column tile][row][4 words]); the leader brings them in three tiles ahead with a bulk copy into a ring of four
-      // boxes (per-thread loads of these words cost one exposed DRAM latency per tile, whatever the prefetch distance)
+      // [column tile][row][4 words]); the leader of group 0 brings them in two tiles ahead with a bulk copy into a ring
+      // of four boxes (per-thread loads of these words cost one exposed DRAM latency per tile, whatever the prefetch
+      // distance). Box (it + 2) & 3 held the words of tile it - 2: once tfull[it] has completed, every epilogue warp
+      // has drained tile it - 2 (the MMAs of tile it waited for that) and read its words long before.
       const int my_tiles_g = (m_tiles - m0 + groups - 1) / groups;
       auto issue_gate = [&](int ti) {
         const int mt = m0 + ti * groups;
@@ -900,40 +907,34 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bulk_load(gbox + (ti & 3) * C::GATE_BOX, g.mask_in + ((size_t)n_t * g.mask_ld + (size_t)mt * BM) * 4, C::GATE_BOX,
                   &auxfull[ti & 3]);
       };
-      if (MASK == 2 && leader)
-        for (int ti = 0; ti < 3 && ti < my_tiles_g; ++ti) issue_gate(ti);
+      if (MASK == 2 && leader && grp == 0)
+        for (int ti = 0; ti < 2 && ti < my_tiles_g; ++ti) issue_gate(ti);
       for (int m_t = m0; m_t < m_tiles; m_t += groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        uint4 gate_w = make_uint4(0u, 0u, 0u, 0u), bits_out = make_uint4(0u, 0u, 0u, 0u);
-        if (MASK == 2) {
-          // box (it + 3) & 3 was last read at the top of tile it - 1; every thread has passed a named barrier since
-          if (leader && it + 3 < my_tiles_g) issue_gate(it + 3);
-          mbar_wait(&auxfull[it & 3], (it >> 2) & 1);
-          gate_w = *reinterpret_cast<const uint4*>(gbox + (it & 3) * C::GATE_BOX + et * 16);
-        }
         GP_T0();
         mbar_wait(&tfull[acc], acc_phase);
         if (leader) GP_ADD(9);
         tc_fence_after();
+        uint2 gate_w = make_uint2(0u, 0u), bits_out = make_uint2(0u, 0u);
+        if (MASK == 2) {
+          if (leader && grp == 0 && it + 2 < my_tiles_g) issue_gate(it + 2);
+          mbar_wait(&auxfull[it & 3], (it >> 2) & 1);
+          gate_w = *reinterpret_cast<const uint2*>(gbox + (it & 3) * C::GATE_BOX + et * 16 + grp * 8);
+        }
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-#ifdef GEMM_DBG_NOEPI
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        continue;
-#endif
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c, ++cidx) {
-          uint8_t* box = epi + (cidx % NBUF) * TILE_BYTES;
+        for (int cc = 0; cc < 2; ++cc, ++k) {
+          const int c = grp * 2 + cc;
+          uint8_t* box = epi + (grp * 2 + (k & 1)) * TILE_BYTES;
           float v[32];
           tmem_ld_32x32(taddr + c * 32, v);
-          if (c == 3) {                                   // accumulator drained
+          if (cc == 1) {                                  // this warp's share of the accumulator is drained
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          const uint32_t gw = c == 0 ? gate_w.x : (c == 1 ? gate_w.y : (c == 2 ? gate_w.z : gate_w.w));
+          const uint32_t gw = cc == 0 ? gate_w.x : gate_w.y;
           uint32_t part[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -953,21 +954,21 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (g.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
             *reinterpret_cast<float4*>(box + et * 128 + ((j4 ^ (et & 7)) << 4)) = o;
           }
-          if (MASK == 1) {   // one coalesced 16-byte store per row and tile (image rows are padded to the tile)
+          if (MASK == 1) {   // one 8-byte store per row, group and tile (image rows are padded to the tile)
             const uint32_t wbits = ((part[0] | part[1]) | (part[2] | part[3])) | ((part[4] | part[5]) | (part[6] | part[7]));
-            if (c == 0) bits_out.x = wbits; else if (c == 1) bits_out.y = wbits; else if (c == 2) bits_out.z = wbits;
+            if (cc == 0) bits_out.x = wbits;
             else {
-              bits_out.w = wbits;
-              *reinterpret_cast<uint4*>(g.mask_out + ((size_t)n_t * g.mask_ld + m_t * BM + et) * 4) = bits_out;
+              bits_out.y = wbits;
+              *reinterpret_cast<uint2*>(g.mask_out + ((size_t)n_t * g.mask_ld + m_t * BM + et) * 4 + grp * 2) = bits_out;
             }
           }
-          // the box written by the NEXT chunk must have been read out by its previous store: at most NBUF-2
-          // older stores may still be in flight when the threads are released
+          // the box the NEXT chunk of this group writes is the one its previous store read: that store must be done
+          // reading before the threads are released
           if (leader) GP_ADD(10);
-          if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 2) : "memory");
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           if (leader) GP_ADD(11);
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (leader) {
             tma_store_2d(&tmD, box, n_t * BN + c * BK, m_t * BM);
             tma_store_commit();
@@ -976,7 +977,13 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (leader) tma_store_wait_all0();
-    } else if (!SPLIT) {
+    }
+  } else if (g.aux_mode != 0 && warp >= 4 && warp < 8) {
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const bool leader = (et == 0);
+    int it = 0;
+    if (!SPLIT) {
       // Streaming epilogue with a second input (residual add / ReLU gate): the aux chunk of a 32-column box is
       // prefetched by TMA three chunks ahead into the ring of 4 boxes, combined in place and stored right away.
       const int my_tiles = (m_tiles - m0 + groups - 1) / groups;
@@ -1405,10 +1412,10 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   }
   if (bres) {
     int grid = (num_sms / g.n_tiles) * g.n_tiles;
-    if (epi.mask_out) gemm_bres_kernel<true, 1><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
-    else if (epi.mask_in) gemm_bres_kernel<false, 2><<<grid, GEMM_THREADS, Bres<false, 2>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
-    else if (g.split) gemm_bres_kernel<true, 0><<<grid, GEMM_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
-    else gemm_bres_kernel<false, 0><<<grid, GEMM_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    if (epi.mask_out) gemm_bres_kernel<true, 1><<<grid, BRES_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else if (epi.mask_in) gemm_bres_kernel<false, 2><<<grid, BRES_THREADS, Bres<false, 2>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else if (g.split) gemm_bres_kernel<true, 0><<<grid, BRES_THREADS, Bres<true>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+    else gemm_bres_kernel<false, 0><<<grid, BRES_THREADS, Bres<false>::SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
     TPC_CHECK_LAUNCH();
     return TPC_OK;
   }
