@@ -157,7 +157,7 @@ def roofline_probe(lib, h, st, M, dev):
     K = 512
     A = torch.randn(M, K, device=dev)
     W = torch.randn(128, K, device=dev) / K ** 0.5
-    Wlo = torch.empty_like(W)   # bf16 correction image of the weights (tpc.h: tpc_gemm_split_image)
+    Wlo = torch.empty_like(W)   # fp16 split image of the weights (tpc.h: tpc_gemm_split_image)
     L.check(lib.tpc_gemm_split_image(h, L.ptr(W), K, 128, K, L.ptr(Wlo), st))
     res = torch.randn(M, 128, device=dev)
     D = torch.empty(M, 128, device=dev)

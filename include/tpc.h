@@ -106,14 +106,14 @@ size_t tpc_a2c_workspace_bytes(const tpc_model* m, int B, int num_bins, int num_
  * ---------------------------------------------------------------------------------------------------- */
 /* D[M,N] = epi(A[M,K] @ Bt[N,K]^T + bias); flags bit0 relu, bit1 layernorm(gamma,beta -> rstd_out),
  * bit2 round outputs to TF32, bit3 atomic split-K accumulate; aux_mode 0 none / 1 add / 2 relu-gate.
- * Bt_corr == NULL: one TF32 pass (operands truncated by the tensor core). Bt_corr = correction image of Bt made by
- * tpc_gemm_split_image: fp32-accurate split product, D = trunc(A).trunc(B) in TF32 plus the two first-order correction
- * terms A.B_lo + A_lo.B (x_lo = x - trunc_tf32(x)) on bf16 operands (the forward passes use this; the backward passes
- * use one pass on TF32-rounded gradients). */
+ * Bt_corr == NULL: one TF32 pass (operands truncated by the tensor core). Bt_corr = split image of Bt made by
+ * tpc_gemm_split_image: fp32-accurate product D = A_h.B_h + A_h.B_r + A_r.B_h with x_h = fp16(x), x_r = fp16(x - x_h)
+ * and fp32 accumulation, ~2^-21 relative (the forward passes use this; the backward passes use one pass on
+ * TF32-rounded gradients). Operands beyond +-65504 saturate. */
 int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
              const float* bias, const float* aux, int ldaux, int aux_mode, const float* gamma, const float* beta,
              float* rstd_out, int flags, int k_splits, const void* Bt_corr, void* stream);
-/* image[2][N][ldb] bf16 = { bf16(Bt), bf16(Bt - trunc_tf32(Bt)) }: N * ldb * 4 bytes, 16-byte aligned, ldb % 8 == 0 */
+/* image[2][N][ldb] fp16 = { B_h = fp16(Bt), B_r = fp16(Bt - B_h) }: N * ldb * 4 bytes, 16-byte aligned, ldb % 8 == 0 */
 int tpc_gemm_split_image(tpc_handle* h, const float* Bt, int ldb, int N, int K, void* image, void* stream);
 /* dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout];  db[Nout] += colsum(dY) when db != NULL */
 int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int M,

@@ -19,7 +19,7 @@ lib.tpc_gemm_split_image.argtypes = [P, P, I, I, I, P, P]
 
 
 def split_image(h, Bt, stream):
-    """bf16 correction image of the weights (tpc.h: tpc_gemm_split_image), as an fp32-sized buffer"""
+    """fp16 split image of the weights (tpc.h: tpc_gemm_split_image), as an fp32-sized buffer"""
     img = torch.empty_like(Bt)
     rc = lib.tpc_gemm_split_image(h, ptr(Bt), Bt.shape[1], Bt.shape[0], Bt.shape[1], ptr(img), stream)
     assert rc == 0, rc
@@ -59,7 +59,7 @@ def main():
         print(f"gemm  M={M} N={N} K={K}: rel-max err {err:.3e} finite={torch.isfinite(D).all().item()}")
         worst = max(worst, err)
 
-    # 3xTF32: fp32-accurate
+    # split product: fp32-accurate
     for (M, N, K) in [(300, 128, 128), (1000, 384, 128), (4096, 128, 512), (260, 128, 19328)]:
         A = torch.randn(M, K, device=dev)
         Bt = torch.randn(N, K, device=dev) / K ** 0.5
@@ -75,7 +75,7 @@ def main():
         print(f"gemm3x M={M} N={N} K={K}: rel-max err {err:.3e}")
         assert err < (2e-5 if K <= 512 else 3e-4), err  # long-K: fp32 accumulation order inside the tensor core
 
-    # weight-resident kernel (K == 128, many row tiles): 1-pass and 3xTF32, bias + relu, aux add / gate
+    # weight-resident kernel (K == 128, many row tiles): 1-pass and split product, bias + relu, aux add / gate
     for (M, N) in [(40000, 128), (39999, 384), (40001, 512)]:
         K = 128
         A = torch.randn(M, K, device=dev)

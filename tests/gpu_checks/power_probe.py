@@ -1,5 +1,5 @@
 """Board power and SM clock while ONE kernel runs back to back for a few seconds (nvidia-smi sampled every 100 ms):
-shows which launches are power-limited (the 3xTF32 forward GEMMs are: the SM clock drops with random operands and not
+shows which launches are power-limited (the forward GEMMs are: the SM clock drops with random operands and not
 with zeros). KIND = ffn2_3x | ffn2_1x | qkv_3x | ffn1_3x | copy;  ZERO=1 uses all-zero operands."""
 import ctypes as C, os, subprocess, sys, time
 import torch

@@ -17,9 +17,9 @@ H = torch.randn(M, 512, device=dev); W1 = torch.randn(512, 128, device=dev) / 11
 W1lo = torch.empty_like(W1); L.check(lib.tpc_gemm_split_image(h, L.ptr(W1), 128, 512, 128, L.ptr(W1lo), st))
 dW = torch.zeros(128, 128, device=dev); db = torch.zeros(128, device=dev)
 for it in range(2):
-    # forward projection 3xTF32 + residual + LayerNorm epilogue
+    # forward projection (split product) + residual + LayerNorm epilogue
     lib.tpc_gemm(h, L.ptr(A), 128, L.ptr(W), 128, L.ptr(D), 128, M, 128, 128, L.ptr(b), L.ptr(res), 128, 1, L.ptr(g), L.ptr(b), L.ptr(rstd), 2, 1, L.ptr(Wlo), st)
-    # forward FFN1 3xTF32 + relu (N=512)
+    # forward FFN1 (split product) + relu (N=512)
     lib.tpc_gemm(h, L.ptr(A), 128, L.ptr(W1), 128, L.ptr(H), 512, M, 512, 128, None, None, 0, 0, None, None, None, 1, 1, L.ptr(W1lo), st)
     # backward dX (1 pass) with add epilogue
     lib.tpc_gemm(h, L.ptr(A), 128, L.ptr(W), 128, L.ptr(D), 128, M, 128, 128, None, L.ptr(res), 128, 1, None, None, None, 4, 1, None, st)

@@ -123,7 +123,7 @@ struct GemmArgs {
   float* atomic_out;
   int ld_out;
   int aux_mode, relu, ln, round_out, atomic;
-  int split;   // 3xTF32: D = A.B + A_lo.B + A.B_lo with A_lo = A - trunc(A) built on chip, B_lo from the weight image
+  int split;   // fp32-accurate FP16 split product (see the file header): activation halves built on chip, weight halves from the image
   float ln_eps;
   uint32_t* mask_out;         // ReLU bit image (weight-resident kernel, MASK template variants)
   const uint32_t* mask_in;
@@ -178,8 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* ring = smem;
   uint8_t* epi = smem + RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
-  uint64_t* full = bars;                 // [MAX_STAGES] stage landed (3xTF32: activation slot landed)
-  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES] stage free (3xTF32: activation slot read by the 4 splitter warps)
+  uint64_t* full = bars;                 // [MAX_STAGES] stage landed (split mode: activation slot landed)
+  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES] stage free (split mode: activation slot read by the 4 splitter warps)
   uint64_t* tfull = bars + 2 * MAX_STAGES;  // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* auxfull = tempty + 2;        // [1]
@@ -192,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // single-pass ring (one stage fewer under a LayerNorm epilogue: its row partials live in the tail of the ring)
   const int nstages = g.ln ? STAGES_1P - 1 : STAGES_1P;
   constexpr int stage_bytes = 2 * TILE_BYTES;
-  uint8_t* bring = ring + NA * TILE_BYTES;      // 3xTF32: weight slots behind the activation slots
+  uint8_t* bring = ring + NA * TILE_BYTES;      // split mode: weight slots behind the activation slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -236,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int step = gridDim.x;
 
   if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer (3xTF32: activation slots only)
+    // ------------------------------------------------------------------ TMA producer (split mode: activation slots only)
     if (lane == 0) {
       const int ns = g.split ? NA : nstages;
       int stage = 0;
@@ -266,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 10) {
-    // ------------------------------------------------------------------ TMA producer of the weight slots (3xTF32)
+    // ------------------------------------------------------------------ TMA producer of the weight slots (split mode)
     // B and B_lo k-blocks come from L2 (every CTA reads the same weight image); their slots are held until the MMAs
     // that read them retire, so they cycle on their own barriers and never hold an activation slot back.
     if (lane == 0 && g.split) {
@@ -288,10 +288,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp < 4) {
-    // ------------------------------------------------------------------ A_lo splitters (3xTF32 mode only)
+    // ------------------------------------------------------------------ splitters (split mode only)
     // thread == tile row: read its 32 fp32 of the k-block from the swizzled smem slot, hand the slot straight back to
-    // the producer (the k-block now lives in registers), then park the raw values and what the tensor core's operand
-    // truncation drops in a TMEM slot as the A operands of the TS-mode MMAs.
+    // the producer (the k-block now lives in registers), then park its two fp16 halves in a TMEM slot as the A operands
+    // of the TS-mode MMAs.
     if (g.split) {
       const int row = threadIdx.x;  // 0..127 == TMEM lane
       int stage = 0, ts = 0;
@@ -351,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           GP_T0();
           if (g.split) {
-            // 3xTF32-accurate product: all MMAs take A from TMEM (parked there by the splitter warps), see
+            // fp32-accurate split product: all MMAs take A from TMEM (parked there by the splitter warps), see
             // issue_split_kblock
             mbar_wait(&bfull[bs], bphase);
             GP_ADD(5);
@@ -660,7 +660,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------
 // Weight-resident variant for K == 128 (every 128-wide projection): a CTA owns ONE 128-column tile of the output,
-// loads that slice of the weights (64 KB, + 64 KB low parts in 3xTF32 mode) into shared memory once and then only
+// loads that slice of the weights (64 KB: fp32 tiles, or the fp16 B_h + B_r tiles in split mode) into shared memory once and then only
 // streams activation tiles. The generic kernel re-reads the weight tile from L2 for every 128-row tile, which at
 // these shapes is 1/3 to 1/2 of all L2->SM traffic (ncu: L2-bound at ~60 % of the HBM rate). CTAs that own
 // different column tiles of the same rows run side by side, so the activation tile comes from HBM once.
@@ -706,7 +706,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;                 // [2]
   uint64_t* auxfull = tempty + 2;               // [4] one per staging box (aux chunk landed)
   uint64_t* bfull = auxfull + 4;                // [1] weights resident
-  uint64_t* tfree = bfull + 1;                  // [NT] 3xTF32: TMEM slot of a split k-block consumed by the MMAs
+  uint64_t* tfree = bfull + 1;                  // [NT] split mode: TMEM slot of a split k-block consumed by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfree + NT);
 
   const int warp = threadIdx.x >> 5;
@@ -1370,7 +1370,7 @@ bool gemm_weight_resident(int M, int N, int K, const GemmEpi& epi, bool split, i
 }
 
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
-                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const void* Bt_lo) {
+                int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream, const void* Bt_corr) {
   TPC_TRY(gemm_tc_init());
   if (M <= 0) return TPC_OK;
   if (N % BN != 0 || K % BK != 0 || K <= 0) return TPC_ERR_SHAPE;
@@ -1389,11 +1389,11 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   g.atomic_out = D; g.ld_out = ldd;
   g.aux_mode = epi.aux_mode; g.relu = epi.relu; g.ln = epi.ln; g.round_out = epi.round_out; g.atomic = epi.atomic;
   g.ln_eps = epi.ln_eps;
-  g.split = Bt_lo ? 1 : 0;
+  g.split = Bt_corr ? 1 : 0;
   CUtensorMap tA, tB, tBlo, tAux, tD;
   TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
   TPC_TRY(get_tmap(tc, Bt, N, K, ldb, BN, 0, &tB));
-  if (Bt_lo) { TPC_TRY(get_tmap_corr(tc, Bt_lo, 2 * N, K, ldb, &tBlo)); } else { tBlo = tB; }
+  if (Bt_corr) { TPC_TRY(get_tmap_corr(tc, Bt_corr, 2 * N, K, ldb, &tBlo)); } else { tBlo = tB; }
   TPC_TRY(get_tmap(tc, D, M, N, ldd, BM, 0, &tD));
   if (epi.aux_mode) {
     if (!epi.aux) return TPC_ERR_ARG;
@@ -1401,11 +1401,11 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   } else {
     tAux = tD;
   }
-  // weight-resident kernel: K == 128, no LayerNorm / split-K, (3xTF32: no aux), enough row tiles per CTA
+  // weight-resident kernel: K == 128, no LayerNorm / split-K, (split mode: no aux), enough row tiles per CTA
   const bool bres = gemm_weight_resident(M, N, K, epi, g.split != 0, num_sms);
   g.mask_out = epi.mask_out; g.mask_in = epi.mask_in; g.mask_ld = epi.mask_ld;
   if (epi.mask_out || epi.mask_in) {
-    // bit images: 16-byte aligned rows, mask_out from the 3xTF32 relu epilogue, mask_in into a single-pass GEMM
+    // bit images: 16-byte aligned rows, mask_out from the split-mode relu epilogue, mask_in into a single-pass GEMM
     // image layout [N / 128][mask_ld rows][4 words], mask_ld = M rounded up to a multiple of 128
     if (!bres || epi.aux_mode || epi.mask_ld < M || epi.mask_ld % BM != 0 || (epi.mask_out && epi.mask_in)) return TPC_ERR_ARG;
     if ((epi.mask_out && !(g.split && epi.relu)) || (epi.mask_in && g.split)) return TPC_ERR_ARG;

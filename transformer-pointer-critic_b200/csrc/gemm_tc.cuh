@@ -21,7 +21,7 @@ struct GemmEpi {
   // ReLU mask as a bit image (weight-resident kernel only, see gemm_weight_resident()), laid out
   // [N / 128 column tiles][mask_ld rows][4 words], mask_ld = M rounded up to a multiple of 128 (so the words one CTA
   // needs for a row tile are 2 KB contiguous): bit j of word c = output column 128 n_t + 32 c + j. mask_out is written
-  // by a 3xTF32 relu epilogue (bit = output positive), mask_in gates the output of a single-pass GEMM
+  // by a split-mode relu epilogue (bit = output positive), mask_in gates the output of a single-pass GEMM
   // (v = bit ? v : 0): the ReLU backward then reads 16 bytes per row tile instead of 512 bytes of saved activation.
   uint32_t* mask_out = nullptr;
   const uint32_t* mask_in = nullptr;
@@ -39,11 +39,11 @@ void tmap_cache_destroy(TmapCache*);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes. idempotent.
 
 // D[M,N] = epi(A[M,K] @ Bt[N,K]^T). K % 32 == 0, N % 128 == 0. k_splits > 1 requires epi.atomic.
-// Bt_corr != nullptr selects the fp32-accurate split product ("3xTF32" with cheaper correction terms):
-//   D = trunc(A).trunc(B) [TF32] + bf16(A).bf16(B_lo) + bf16(A_lo).bf16(B) [kind::f16], x_lo = x - trunc_tf32(x).
-// Bt holds the raw fp32 weights (the tensor core truncates them), Bt_corr the bf16 correction image
-// [2][N][ldb] = {bf16(B), bf16(B_lo)} made by build_split_image (same byte size as an fp32 [N][ldb] matrix); the
-// A-side parts are split on chip. Error ~2^-19 relative (bf16 keeps 8 bits of terms that are 2^-11 of the product).
+// Bt_corr != nullptr selects the fp32-accurate split product:
+//   D = A_h.B_h + A_h.B_r + A_r.B_h on kind::f16 MMAs with fp32 accumulation, x_h = fp16(x), x_r = fp16(x - x_h).
+// Bt_corr is the fp16 split image [2][N][ldb] = {B_h, B_r} made by build_split_image (same byte size as an fp32
+// [N][ldb] matrix; Bt itself is then only used for its shape); the activation halves are split on chip. Error ~2^-21
+// relative; values beyond +-65504 saturate (fp16 range), parts below 6e-5 keep an absolute error <= 3e-8.
 int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N,
                 int K, const GemmEpi& epi, int k_splits, int num_sms, cudaStream_t stream,
                 const void* Bt_corr = nullptr);

@@ -32,7 +32,7 @@ __global__ void small_dense_fwd_kernel(const float* __restrict__ x, int ldx, con
     // order only; fp32 fma chain keeps |err| ~1e-7
     acc.x = fmaf(xf, w.x, acc.x); acc.y = fmaf(xf, w.y, acc.y); acc.z = fmaf(xf, w.z, acc.z); acc.w = fmaf(xf, w.w, acc.w);
   }
-  reinterpret_cast<float4*>(out + (size_t)r * 128)[c4] = acc;   // forward activations stay fp32 (3xTF32 consumers)
+  reinterpret_cast<float4*>(out + (size_t)r * 128)[c4] = acc;   // forward activations stay fp32 (fp32-accurate consumers)
 }
 
 __global__ void small_dense_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ extra, int rows,

@@ -71,7 +71,7 @@ int gemm(Ctx& cx, const float* A, int lda, const float* Bt, int ldb, float* D, i
   return launch_gemm(cx.tc(), A, lda, Bt, ldb, D, ldd, M, N, K, e, ks, cx.sms(), cx.st);
 }
 
-// forward GEMM: 3xTF32 (fp32-accurate); Bt must be a "_t" entry of the weight image, outputs are not rounded
+// forward GEMM: fp32-accurate FP16 split product; Bt must be a "_t" entry of the weight image, outputs are not rounded
 int gemm_fwd(Ctx& cx, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
              GemmEpi e, int ks = 1) {
   if (cx.dry()) return TPC_OK;
@@ -296,7 +296,7 @@ int decoder_forward(Ctx& cx, const float* dec_input, const float* ptr_mask, cons
     d.q2 = ar.f((size_t)C * 128); d.kvw = ar.f((size_t)C * S * 384); d.pc = ar.f((size_t)C * 8 * S);
     d.ctx = ar.f((size_t)C * 128); d.o2 = ar.f((size_t)C * 128); d.rstd2 = ar.f(C);
     d.f = ar.f((size_t)C * dff); d.o3 = ar.f((size_t)C * 128); d.rstd3 = ar.f(C);
-    // K2 | V2 | W2e of every encoder token: the one GEMM-shaped product of the decoder (tensor cores, 3xTF32)
+    // K2 | V2 | W2e of every encoder token: the one GEMM-shaped product of the decoder (tensor cores, fp32-accurate split product)
     TPC_TRY(gemm_fwd(cx, a.enc.enc_out, 128, cx.W + lp.s.wkvp_t, 128, d.kvw, 384, C * S, 384, 128,
                  epi_bias(cx.W + lp.s.bkvp)));
     // everything on the single decoder token: one fused kernel (csrc/kernels.cuh, DecChainArgs)
