@@ -14,6 +14,11 @@ def test_tcgen05_gemm_and_wgrad_kernels():
     check_gemm.main()        # asserts inside: TF32 1-pass < 2e-3, split product < 2e-5 (K<=512), fused epilogues, wgrad + bias
 
 
+def test_split_image_bit_exact_and_fp16_range_behaviour():
+    from tests.gpu_checks import check_gemm
+    check_gemm.check_split_image_and_range()
+
+
 def test_actor_critic_forward_and_gradients_vs_oracle():
     from tests.gpu_checks import check_model
     worst = check_model.main()
