@@ -151,7 +151,7 @@ def roofline_probe(lib, h, st, M, dev):
     """The launch of the dominant kernel that the roofline is quoted on: gemm_tc_kernel as the critic's second FFN
     layer (K = 512 -> 128, fp32-accurate FP16-split product) with the residual add + LayerNorm epilogue, M tokens of one update chunk.
     Returns (callable, algorithmic bytes per launch, label). tests/gpu_checks/roofline_probe.py runs the same
-    launch under ncu for `profiles/gemm_tc_traffic.json`."""
+    launch under ncu for `profiles/r02f_ncu_full_gemm_tc_ffn2.json`."""
     import torch
     from tpc_b200 import lib as L
     K = 512
@@ -374,10 +374,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_gemm = e0.elapsed_time(e1) / reps / 1e3
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture of the
+    # current kernel (tests/gpu_checks/run_profiles_r02f.sh)
+    tpath = os.path.join(ROOT, "profiles", "r02f_ncu_full_gemm_tc_ffn2.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath))["gemm_tc_kernel"].get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     # tensor-core view of the whole step: dense algorithmic FLOPs per decision x decisions/s per GPU against

@@ -88,7 +88,8 @@ int tpc_param_layout(const tpc_model* m, int which, int64_t* offsets, int64_t* s
  * kernels are [rows][cols] = [in][out], 1-D tensors report cols = 0. Used by the weight interchange
  * (agents/agent.py:289-294: Keras attribute paths of a TF checkpoint). */
 int tpc_param_info(const tpc_model* m, int which, int index, char* name, int name_capacity, int64_t* rows, int64_t* cols);
-/* floats in the kernel-side weight image (transposed / fused / TF32-rounded copies) */
+/* floats in the kernel-side weight image: transposed / fused copies of the forward weights with their fp16 split images
+ * (see tpc_gemm), TF32-rounded copies for the backward GEMMs */
 size_t tpc_shadow_count(const tpc_model* m, int which);
 /* rebuild the weight image after params changed (after load_weights / every optimizer step) */
 int tpc_prepare_weights(tpc_model* m, int which, const float* params, float* shadow, void* stream);

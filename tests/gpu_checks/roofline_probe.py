@@ -1,5 +1,5 @@
 """The roofline launch of bench.py (gemm_tc_kernel, FFN2 + residual + LayerNorm at one update chunk) on its own, for
-`ncu --set full -k regex:gemm_tc -c 1`: dram__bytes_read.sum + dram__bytes_write.sum go to profiles/gemm_tc_traffic.json."""
+`ncu --set full -k regex:gemm_tc -c 1`: dram__bytes_read.sum + dram__bytes_write.sum go to profiles/r02f_ncu_full_gemm_tc_ffn2.json (round 1: profiles/gemm_tc_traffic.json)."""
 import ctypes as C, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
