@@ -116,6 +116,15 @@ int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, f
              float* rstd_out, int flags, int k_splits, const void* Bt_corr, void* stream);
 /* image[2][N][ldb] fp16 = { B_h = fp16(Bt), B_r = fp16(Bt - B_h) }: N * ldb * 4 bytes, 16-byte aligned, ldb % 8 == 0 */
 int tpc_gemm_split_image(tpc_handle* h, const float* Bt, int ldb, int N, int K, void* image, void* stream);
+/* Backward GEMM with the LayerNorm backward fused into its epilogue (N = 128, one TF32 pass): with
+ * dy = A[M,K] @ Bt[128,K]^T (+ aux[M,128] when aux != NULL) the gradient w.r.t. a LayerNorm output y = LN(pre),
+ *   D[M,128] = dpre = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (y - beta) / gamma,
+ *   dgamma[128] += sum_rows(dy * xhat),  dbeta[128] += sum_rows(dy)
+ * (tf.keras LayerNormalization under tf.GradientTape, agents/trainer.py:115-141; D is RN-rounded to TF32 because it
+ * feeds the next backward GEMMs). dy itself is never written. */
+int tpc_gemm_ln_bwd(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int K,
+                    const float* aux, int ldaux, const float* y, const float* rstd, const float* gamma,
+                    const float* beta, float* dgamma, float* dbeta, void* stream);
 /* dW[Kin,Nout] += X[M,Kin]^T @ dY[M,Nout];  db[Nout] += colsum(dY) when db != NULL */
 int tpc_wgrad(tpc_handle* h, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int M,
               int Kin, int Nout, void* stream);

@@ -252,3 +252,81 @@ def check_split_image_and_range():
     assert out["tiny_abs"] < 128 ** 0.5 * 4 * 3e-8 * 4, out
     lib.tpc_destroy(h)
     return out
+
+
+lib.tpc_gemm_ln_bwd.argtypes = [P, P, I, P, I, P, I, I, I, P, I, P, P, P, P, P, P, P]
+
+
+def check_gemm_ln_bwd(timing=False):
+    """tpc_gemm_ln_bwd (backward GEMM whose epilogue is the LayerNorm backward) against torch autograd in fp64:
+    pre -> y = LayerNorm(pre); dy = A @ Bt^T + aux; the kernel must return d(pre), and add d(gamma), d(beta)."""
+    dev = torch.device("cuda:0")
+    h = P()
+    assert lib.tpc_create(ctypes.byref(h)) == 0
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    torch.manual_seed(11)
+    out = {}
+    for (M, K, with_aux) in [(128, 128, True), (1000, 512, True), (40001, 384, True), (777, 128, False), (19000, 512, False)]:
+        pre = (torch.randn(M, 128, device=dev) * 2 + 0.3).double().requires_grad_(True)
+        gamma = (1 + 0.2 * torch.randn(128, device=dev)).double().requires_grad_(True)
+        beta = (0.1 * torch.randn(128, device=dev)).double().requires_grad_(True)
+        y64 = torch.nn.functional.layer_norm(pre, (128,), gamma, beta, 1e-6)
+        rstd = (1.0 / torch.sqrt(pre.var(dim=1, unbiased=False) + 1e-6)).float().contiguous()
+        A = torch.randn(M, K, device=dev)
+        Bt = torch.randn(128, K, device=dev) / K ** 0.5
+        aux = torch.randn(M, 128, device=dev) if with_aux else None
+        dy = A.double() @ Bt.double().T + (aux.double() if with_aux else 0.0)
+        y64.backward(dy)
+        y = y64.detach().float().contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        D = torch.full((M, 128), float("nan"), device=dev)
+        dg = torch.zeros(128, device=dev)
+        db = torch.zeros(128, device=dev)
+        rc = lib.tpc_gemm_ln_bwd(h, ptr(A), K, ptr(Bt), K, ptr(D), 128, M, K, ptr(aux), 128, ptr(y), ptr(rstd), ptr(g32),
+                                 ptr(b32), ptr(dg), ptr(db), stream)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        assert torch.isfinite(D).all()
+        e_d = ((D.double() - pre.grad).abs().max() / pre.grad.abs().max()).item()
+        e_g = ((dg.double() - gamma.grad).abs().max() / gamma.grad.abs().max()).item()
+        e_b = ((db.double() - beta.grad).abs().max() / beta.grad.abs().max()).item()
+        print(f"gemm + LN backward M={M} K={K} aux={with_aux}: dpre {e_d:.3e} dgamma {e_g:.3e} dbeta {e_b:.3e}")
+        out[(M, K, with_aux)] = (e_d, e_g, e_b)
+        # one TF32 pass on unrounded operands + TF32-rounded output: the class of the other backward GEMMs (2e-3)
+        assert e_d < 3e-3 and e_g < 3e-3 and e_b < 3e-3, (M, K, e_d, e_g, e_b)
+    if timing:
+        for K in (512, 384):
+            M = 1546240
+            A = torch.randn(M, K, device=dev)
+            Bt = torch.randn(128, K, device=dev) / K ** 0.5
+            aux = torch.randn(M, 128, device=dev)
+            y = torch.randn(M, 128, device=dev)
+            rstd = torch.rand(M, device=dev) + 0.5
+            g32 = torch.ones(128, device=dev)
+            b32 = torch.zeros(128, device=dev)
+            D = torch.empty(M, 128, device=dev)
+            dg = torch.zeros(128, device=dev)
+            db = torch.zeros(128, device=dev)
+
+            def fused():
+                lib.tpc_gemm_ln_bwd(h, ptr(A), K, ptr(Bt), K, ptr(D), 128, M, K, ptr(aux), 128, ptr(y), ptr(rstd), ptr(g32),
+                                    ptr(b32), ptr(dg), ptr(db), stream)
+
+            def plain():
+                lib.tpc_gemm(h, ptr(A), K, ptr(Bt), K, ptr(D), 128, M, 128, K, None, ptr(aux), 128, 1, None, None, None, 4, 1,
+                             None, stream)
+
+            for name, fn in (("gemm + aux add (unfused producer)", plain), ("gemm + aux add + LN backward epilogue", fused)):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+                for _ in range(10):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / 10 * 1e3
+                byts = M * (K + 128 * (2 if fn is plain else 3)) * 4   # A + aux + D (+ the saved LayerNorm output)
+                print(f"  K={K} M={M} {name}: {us:.0f} us, {byts / us / 1e6:.2f} TB/s of its own bytes")
+    lib.tpc_destroy(h)
+    return out

@@ -19,6 +19,11 @@ def test_split_image_bit_exact_and_fp16_range_behaviour():
     check_gemm.check_split_image_and_range()
 
 
+def test_gemm_with_layernorm_backward_epilogue_vs_autograd_fp64():
+    from tests.gpu_checks import check_gemm
+    check_gemm.check_gemm_ln_bwd()   # d(pre), d(gamma), d(beta) within 3e-3 (one TF32 pass), ragged M, with / without aux
+
+
 def test_actor_critic_forward_and_gradients_vs_oracle():
     from tests.gpu_checks import check_model
     worst = check_model.main()

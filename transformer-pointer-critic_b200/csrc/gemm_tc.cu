@@ -128,6 +128,10 @@ struct GemmArgs {
   uint32_t* mask_out;         // ReLU bit image (weight-resident kernel, MASK template variants)
   const uint32_t* mask_in;
   int mask_ld;
+  const float* lnb_y;         // LayerNorm-backward epilogue (see GemmEpi)
+  const float* lnb_rstd;
+  float* lnb_dgamma;
+  float* lnb_dbeta;
 };
 
 // byte offset of (row, col) inside the staging tile: 4 boxes [128 rows][32 cols], rows of 128 B, 16-byte chunks
@@ -169,6 +173,9 @@ __device__ __forceinline__ void issue_split_kblock(uint32_t tmem_d, uint32_t tme
   }
 }
 
+// LNB: the LayerNorm-BACKWARD epilogue (GemmEpi::lnb_y) as its own instantiation, so that the common one keeps its
+// registers (every epilogue variant of this kernel sits at the 128-register cap of 480 threads).
+template <bool LNB>
 __global__ void __launch_bounds__(GEMM_TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmAux,
@@ -220,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], g.ln ? 8 : 4);   // one arrival per epilogue warp (LayerNorm: two warpgroups)
+      mbar_init(&tempty[a], (g.ln || LNB) ? 8 : 4);   // one arrival per epilogue warp (LayerNorm forward / backward: two warpgroups)
     }
     mbar_init(auxfull, 1);
     for (int a = 0; a < 4; ++a) mbar_init(&auxbox[a], 1);
@@ -396,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #endif
     }
-  } else if (g.ln && ((warp >= 4 && warp < 8) || warp >= 11)) {
+  } else if (!LNB && g.ln && ((warp >= 4 && warp < 8) || warp >= 11)) {
     // ------------------------------------------------------------------ LayerNorm epilogue (256 threads)
     // Two warpgroups share a tile: thread (row, half) owns 64 columns of accumulator row `et` (TMEM lane quarter
     // warp % 4 either way), so a row lives in 64 registers instead of 128 -- the one-thread-per-row version could not
@@ -493,7 +500,124 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar_sync(1, 256);
     }
     if (leader) tma_store_wait_all0();
-  } else if (warp >= 4 && warp < 8) {
+  } else if (LNB && ((warp >= 4 && warp < 8) || warp >= 11)) {
+    // ------------------------------------------------------------------ LayerNorm-BACKWARD epilogue (256 threads)
+    // Phase 1 (thread = accumulator row x 64-column half, as TMEM dictates): dy = accumulator + aux, written back over
+    // the aux tile in the staging buffer. Phase 2 (warp = row, lane = 4 columns, the layout of the standalone ln_bwd
+    // kernel): row means by warp shuffles, dpre written over dy, column sums for dgamma / dbeta kept in registers
+    // across all tiles of the CTA and reduced once at the end. The rows of y for the NEXT tile are requested before
+    // the accumulator wait, so their latency hides behind the main loop.
+    const int q = warp & 3;
+    const int half = warp >= 11 ? 1 : 0;
+    const int et = q * 32 + lane;
+    const int ew = half * 4 + q;                // epilogue warp 0..7: rows ew * 16 .. + 15 of the tile in phase 2
+    const bool leader = (warp == 4 && lane == 0);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(g.gamma) + lane);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(g.beta) + lane);
+    float4 ig;
+    ig.x = gm.x != 0.f ? 1.f / gm.x : 0.f; ig.y = gm.y != 0.f ? 1.f / gm.y : 0.f;
+    ig.z = gm.z != 0.f ? 1.f / gm.z : 0.f; ig.w = gm.w != 0.f ? 1.f / gm.w : 0.f;
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t aux_phase = 0;
+    int it = 0;
+    if (g.aux_mode && leader && first < g.num_items) {
+      const int m_t = first / g.n_tiles;
+      mbar_expect_tx(auxfull, EPI_BYTES);
+      for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, j * BK, m_t * BM);
+    }
+    for (int item = first; item < g.num_items; item += step, ++it) {
+      const int m_t = item / g.n_tiles;         // n_tiles == 1, k_splits == 1 in this mode
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      // the saved LayerNorm output rows of this warp's 16 phase-2 rows (and their 1/sigma), in flight during the wait
+      float4 yv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = m_t * BM + ew * 16 + i;
+        yv[i] = r < g.M ? __ldg(reinterpret_cast<const float4*>(g.lnb_y + (size_t)r * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int rl = m_t * BM + ew * 16 + (lane & 15);          // lane i (and i + 16) keeps 1/sigma of row i
+      const float rs_lane = rl < g.M ? __ldg(g.lnb_rstd + rl) : 0.f;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (g.aux_mode) {
+        mbar_wait(auxfull, aux_phase);
+        aux_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4* slot = reinterpret_cast<float4*>(epi + epi_off(et, half * 16 + c * 8 + j4));
+          float4 o = make_float4(v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          if (g.aux_mode == 1) { const float4 a = *slot; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+          *slot = o;
+        }
+      }
+      named_bar_sync(2, 256);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int rt = ew * 16 + i;
+        float4* slot = reinterpret_cast<float4*>(epi + epi_off(rt, lane));
+        const float4 d = *slot;
+        const float4 o = yv[i];
+        float4 xh, gg;
+        xh.x = (o.x - bt.x) * ig.x; xh.y = (o.y - bt.y) * ig.y; xh.z = (o.z - bt.z) * ig.z; xh.w = (o.w - bt.w) * ig.w;
+        gg.x = d.x * gm.x; gg.y = d.y * gm.y; gg.z = d.z * gm.z; gg.w = d.w * gm.w;
+        const float mg = warp_sum((gg.x + gg.y) + (gg.z + gg.w)) * (1.f / 128.f);
+        const float mgx = warp_sum((gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w)) * (1.f / 128.f);
+        const float rsi = __shfl_sync(0xffffffffu, rs_lane, i);
+        float4 dp;
+        dp.x = rsi * (gg.x - mg - xh.x * mgx); dp.y = rsi * (gg.y - mg - xh.y * mgx);
+        dp.z = rsi * (gg.z - mg - xh.z * mgx); dp.w = rsi * (gg.w - mg - xh.w * mgx);
+        if (g.round_out) { dp.x = tf32_rn(dp.x); dp.y = tf32_rn(dp.y); dp.z = tf32_rn(dp.z); dp.w = tf32_rn(dp.w); }
+        *slot = dp;
+        ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
+        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (leader) {
+        for (int j = 0; j < 4; ++j) tma_store_2d(&tmD, epi + j * TILE_BYTES, j * BK, m_t * BM);
+        tma_store_commit();
+        tma_store_wait_read0();  // staging tile may be overwritten
+        const int next = item + step;
+        if (g.aux_mode && next < g.num_items) {
+          const int nm = next / g.n_tiles;
+          mbar_expect_tx(auxfull, EPI_BYTES);
+          for (int j = 0; j < 4; ++j) tma_load_2d(epi + j * TILE_BYTES, &tmAux, auxfull, j * BK, nm * BM);
+        }
+      }
+      named_bar_sync(1, 256);
+    }
+    if (leader) tma_store_wait_all0();
+    // column sums: the 8 epilogue warps meet in the (now free) staging tile, one warp adds them to global memory
+    named_bar_sync(1, 256);
+    float4* sg = reinterpret_cast<float4*>(epi);
+    float4* sb = sg + 8 * 32;
+    sg[ew * 32 + lane] = ag;
+    sb[ew * 32 + lane] = ab;
+    named_bar_sync(1, 256);
+    if (ew == 0) {
+      for (int w = 1; w < 8; ++w) {
+        const float4 x = sg[w * 32 + lane], y = sb[w * 32 + lane];
+        ag.x += x.x; ag.y += x.y; ag.z += x.z; ag.w += x.w;
+        ab.x += y.x; ab.y += y.y; ab.z += y.z; ab.w += y.w;
+      }
+      atomicAdd(g.lnb_dgamma + lane * 4 + 0, ag.x); atomicAdd(g.lnb_dgamma + lane * 4 + 1, ag.y);
+      atomicAdd(g.lnb_dgamma + lane * 4 + 2, ag.z); atomicAdd(g.lnb_dgamma + lane * 4 + 3, ag.w);
+      atomicAdd(g.lnb_dbeta + lane * 4 + 0, ab.x); atomicAdd(g.lnb_dbeta + lane * 4 + 1, ab.y);
+      atomicAdd(g.lnb_dbeta + lane * 4 + 2, ab.z); atomicAdd(g.lnb_dbeta + lane * 4 + 3, ab.w);
+    }
+  } else if (!LNB && warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int et = threadIdx.x - 128;          // 0..127 == accumulator row inside the tile == TMEM lane
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
@@ -1255,7 +1379,8 @@ int gemm_tc_init() {
       return;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_bres_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bres<true>::SMEM);
       if (e == cudaSuccess)
@@ -1378,6 +1503,9 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   if (k_splits < 1) k_splits = 1;
   if (k_splits > 1 && !epi.atomic) return TPC_ERR_ARG;
   if (epi.atomic && (epi.aux_mode || epi.ln || epi.relu || epi.bias)) return TPC_ERR_ARG;
+  if (epi.lnb_y && (N != BN || epi.ln || epi.atomic || epi.relu || epi.bias || epi.aux_mode == 2 || Bt_corr || !epi.lnb_rstd ||
+                    !epi.lnb_dgamma || !epi.lnb_dbeta || !epi.gamma || !epi.beta || epi.mask_in || epi.mask_out))
+    return TPC_ERR_ARG;
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
   g.n_tiles = N / BN;
@@ -1389,6 +1517,7 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   g.atomic_out = D; g.ld_out = ldd;
   g.aux_mode = epi.aux_mode; g.relu = epi.relu; g.ln = epi.ln; g.round_out = epi.round_out; g.atomic = epi.atomic;
   g.ln_eps = epi.ln_eps;
+  g.lnb_y = epi.lnb_y; g.lnb_rstd = epi.lnb_rstd; g.lnb_dgamma = epi.lnb_dgamma; g.lnb_dbeta = epi.lnb_dbeta;
   g.split = Bt_corr ? 1 : 0;
   CUtensorMap tA, tB, tBlo, tAux, tD;
   TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
@@ -1402,7 +1531,7 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     tAux = tD;
   }
   // weight-resident kernel: K == 128, no LayerNorm / split-K, (split mode: no aux), enough row tiles per CTA
-  const bool bres = gemm_weight_resident(M, N, K, epi, g.split != 0, num_sms);
+  const bool bres = !epi.lnb_y && gemm_weight_resident(M, N, K, epi, g.split != 0, num_sms);
   g.mask_out = epi.mask_out; g.mask_in = epi.mask_in; g.mask_ld = epi.mask_ld;
   if (epi.mask_out || epi.mask_in) {
     // bit images: 16-byte aligned rows, mask_out from the split-mode relu epilogue, mask_in into a single-pass GEMM
@@ -1420,7 +1549,8 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
     return TPC_OK;
   }
   const int grid = g.num_items < num_sms ? g.num_items : num_sms;
-  gemm_tc_kernel<<<grid, GEMM_TC_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+  if (epi.lnb_y) gemm_tc_kernel<true><<<grid, GEMM_TC_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
+  else gemm_tc_kernel<false><<<grid, GEMM_TC_THREADS, GEMM_SMEM, stream>>>(tA, tB, tBlo, tAux, tD, g);
   TPC_CHECK_LAUNCH();
   return TPC_OK;
 }

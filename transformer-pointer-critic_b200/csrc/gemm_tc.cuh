@@ -26,6 +26,16 @@ struct GemmEpi {
   uint32_t* mask_out = nullptr;
   const uint32_t* mask_in = nullptr;
   int mask_ld = 0;
+  // LayerNorm BACKWARD fused into the epilogue (generic kernel, N == 128, single pass): the GEMM result (+ aux) is the
+  // gradient w.r.t. a LayerNorm output y = LN(pre); instead of storing it, the epilogue stores the gradient w.r.t. pre,
+  //   g = dy * gamma, xhat = (y - beta) / gamma, dpre = rstd * (g - mean(g) - xhat * mean(g * xhat))
+  // and accumulates dgamma += sum_rows(dy * xhat), dbeta += sum_rows(dy) (kernels.cuh: ln_bwd, which this replaces
+  // where the producer of dy is such a GEMM: dy is then never written to or re-read from HBM).
+  // lnb_y [M,128] = the saved LayerNorm output, lnb_rstd [M]; gamma / beta above are the LayerNorm parameters.
+  const float* lnb_y = nullptr;
+  const float* lnb_rstd = nullptr;
+  float* lnb_dgamma = nullptr;
+  float* lnb_dbeta = nullptr;
 };
 
 // true when launch_gemm routes this shape to the weight-resident kernel (the one that supports mask_out / mask_in)

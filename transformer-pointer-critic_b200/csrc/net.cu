@@ -140,14 +140,36 @@ int enc_layer_forward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int L
 
 struct BwdScratch { float *dA, *dB, *dQKV; };
 
-// dout: gradient w.r.t. out2, rows addressed through dmap; dx receives the gradient w.r.t. x
+// LayerNorm backward fused into the epilogue of the GEMM that produces the gradient of the LayerNorm output
+// (GemmEpi::lnb_y, gemm_tc.cu): TPC_FUSE_LNB=0 falls back to the stand-alone ln_bwd launches (A / B runs, tests).
+bool fuse_lnb() {
+  static const bool on = [] { const char* v = getenv("TPC_FUSE_LNB"); return !(v && v[0] == '0'); }();
+  return on;
+}
+GemmEpi epi_lnb(const Ctx& cx, const float* aux, const float* y, const float* rstd, const LnP& ln) {
+  GemmEpi e;
+  e.aux = aux; e.ldaux = 128; e.aux_mode = 1;
+  e.gamma = cx.P + ln.g; e.beta = cx.P + ln.b;
+  e.lnb_y = y; e.lnb_rstd = rstd; e.lnb_dgamma = cx.G + ln.g; e.lnb_dbeta = cx.G + ln.b;
+  return e;
+}
+struct PrevLn { const LnP* ln; const float* rstd; };   // the LayerNorm that produced this layer's input x
+
+// dout: gradient w.r.t. out2, rows addressed through dmap -- or, with dout_is_dpre2, already the gradient w.r.t. the
+// input of LayerNorm 2 (the layer above fused that LayerNorm backward into its dx GEMM). dx receives the gradient
+// w.r.t. x, or with prev != nullptr the gradient w.r.t. the input of the LayerNorm that produced x.
 int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int Lt, MaskRef mk, EncLayerActs& a,
-                       const float* dout, RowMap dmap, float* dx, BwdScratch& s) {
+                       const float* dout, RowMap dmap, float* dx, BwdScratch& s, bool dout_is_dpre2 = false,
+                       const PrevLn* prev = nullptr) {
   const int rows = C * Lt, dff = cx.L->dff;
   const RowMap ident{Lt, Lt, 0};
-  RUN(ln_bwd(dout, dmap, a.out2, a.rstd2, cx.P + lp.ln2.g, cx.P + lp.ln2.b, rows, s.dA, cx.G + lp.ln2.g,
-             cx.G + lp.ln2.b, cx.st));
-  TPC_TRY(dense_grads(cx, a.h, dff, s.dA, 128, rows, lp.f2));
+  const float* dpre2 = dout;
+  if (!dout_is_dpre2) {
+    RUN(ln_bwd(dout, dmap, a.out2, a.rstd2, cx.P + lp.ln2.g, cx.P + lp.ln2.b, rows, s.dA, cx.G + lp.ln2.g,
+               cx.G + lp.ln2.b, cx.st));
+    dpre2 = s.dA;
+  }
+  TPC_TRY(dense_grads(cx, a.h, dff, dpre2, 128, rows, lp.f2));
   {  // dH = (dpre2 @ W2^T) * (h > 0), written over h
     GemmEpi e;
     if (a.has_mask && gemm_weight_resident(rows, dff, 128, e, false, cx.sms())) {
@@ -155,18 +177,53 @@ int enc_layer_backward(Ctx& cx, const EncLayerP& lp, const float* x, int C, int 
     } else {
       e.aux = a.h; e.ldaux = dff; e.aux_mode = 2;
     }
-    TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.w2_c, 128, a.h, dff, rows, dff, 128, e));
+    TPC_TRY(gemm(cx, dpre2, 128, cx.W + lp.s.w2_c, 128, a.h, dff, rows, dff, 128, e));
   }
   TPC_TRY(dense_grads(cx, a.out1, 128, a.h, dff, rows, lp.f1));
-  TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w1_c, dff, s.dB, 128, rows, 128, dff, epi_add(s.dA, 128)));  // dout1
-  RUN(ln_bwd(s.dB, ident, a.out1, a.rstd1, cx.P + lp.ln1.g, cx.P + lp.ln1.b, rows, s.dA, cx.G + lp.ln1.g,
-             cx.G + lp.ln1.b, cx.st));
-  TPC_TRY(dense_grads(cx, a.att, 128, s.dA, 128, rows, lp.mha.o));
-  TPC_TRY(gemm(cx, s.dA, 128, cx.W + lp.s.wo_c, 128, s.dB, 128, rows, 128, 128, GemmEpi()));          // datt
-  RUN(attention_bwd(a.qkv, a.att, a.lse, s.dB, mk.mask, mk.mS, mk.m0, C, Lt, s.dQKV, cx.st, mk.split, mk.gap));
+  const float* dpre1;
+  float* tmp;
+  if (fuse_lnb()) {
+    // dout1 = dH @ W1^T + dpre2 never reaches HBM: the epilogue turns it into dpre1
+    TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w1_c, dff, s.dB, 128, rows, 128, dff,
+                 epi_lnb(cx, dpre2, a.out1, a.rstd1, lp.ln1)));
+    dpre1 = s.dB; tmp = s.dA;
+  } else {
+    TPC_TRY(gemm(cx, a.h, dff, cx.W + lp.s.w1_c, dff, s.dB, 128, rows, 128, dff, epi_add(dpre2, 128)));  // dout1
+    RUN(ln_bwd(s.dB, ident, a.out1, a.rstd1, cx.P + lp.ln1.g, cx.P + lp.ln1.b, rows, s.dA, cx.G + lp.ln1.g,
+               cx.G + lp.ln1.b, cx.st));
+    dpre1 = s.dA; tmp = s.dB;
+  }
+  TPC_TRY(dense_grads(cx, a.att, 128, dpre1, 128, rows, lp.mha.o));
+  TPC_TRY(gemm(cx, dpre1, 128, cx.W + lp.s.wo_c, 128, tmp, 128, rows, 128, 128, GemmEpi()));          // datt
+  RUN(attention_bwd(a.qkv, a.att, a.lse, tmp, mk.mask, mk.mS, mk.m0, C, Lt, s.dQKV, cx.st, mk.split, mk.gap));
   const DenseP* qkv[3] = {&lp.mha.q, &lp.mha.k, &lp.mha.v};
   TPC_TRY(fused_grads(cx, x, 128, s.dQKV, 384, rows, qkv, 3));
-  TPC_TRY(gemm(cx, s.dQKV, 384, cx.W + lp.s.wqkv_c, 384, dx, 128, rows, 128, 384, epi_add(s.dA, 128)));  // dx
+  TPC_TRY(gemm(cx, s.dQKV, 384, cx.W + lp.s.wqkv_c, 384, dx, 128, rows, 128, 384,
+               prev ? epi_lnb(cx, dpre1, x, prev->rstd, *prev->ln) : epi_add(dpre1, 128)));  // dx (or dpre2 of the layer below)
+  return TPC_OK;
+}
+
+// backward through one stack of encoder layers (top layer first). d_top: gradient w.r.t. the stack's output, rows through
+// dm; x0: the stack's input; bufs: two ping-pong buffers. Returns the buffer holding the gradient w.r.t. x0.
+int enc_stack_backward(Ctx& cx, const std::vector<EncLayerP>& lps, std::vector<EncLayerActs>& acts, const float* x0,
+                       int C, int Lt, MaskRef mk, const float* d_top, RowMap dm, float* const bufs[2], BwdScratch& s,
+                       const float** d_x0) {
+  const int nl = (int)lps.size();
+  const float* dc = d_top;
+  bool is_dpre2 = false;
+  int bi = 0;
+  for (int i = nl - 1; i >= 0; --i) {
+    const float* x = i == 0 ? x0 : acts[i - 1].out2;
+    PrevLn pv;
+    const bool fuse_prev = i > 0 && fuse_lnb();
+    if (fuse_prev) { pv.ln = &lps[i - 1].ln2; pv.rstd = acts[i - 1].rstd2; }
+    TPC_TRY(enc_layer_backward(cx, lps[i], x, C, Lt, mk, acts[i], dc, dm, bufs[bi], s, is_dpre2, fuse_prev ? &pv : nullptr));
+    dc = bufs[bi];
+    dm = RowMap{Lt, Lt, 0};
+    is_dpre2 = fuse_prev;
+    bi ^= 1;
+  }
+  *d_x0 = dc;
   return TPC_OK;
 }
 
@@ -216,50 +273,23 @@ int encoder_backward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, 
   s.dQKV = ar.f((size_t)C * Se * 384);
   float* dx0 = ar.f((size_t)C * Se * 128);
   float* dx1 = ar.f((size_t)C * Se * 128);
-  const float* dcur = d_enc;
-  float* dnext = dx0;
-  for (int i = nl - 1; i >= 0; --i) {
-    const float* x = i == 0 ? a.cat : a.joint[i - 1].out2;
-    TPC_TRY(enc_layer_backward(cx, L.enc.joint[i], x, C, Se, MaskRef{mha_mask, S, 0, N, r0}, a.joint[i], dcur,
-                               RowMap{Se, Se, 0}, dnext, s));
-    dcur = dnext;
-    dnext = (dnext == dx0) ? dx1 : dx0;
-  }
-  const float* dcat = dcur;          // [C*S,128]
-  float* other = dnext;              // free ping-pong buffer
-  float* third = const_cast<float*>(d_enc);  // d_enc is consumed: reuse as a third buffer
+  float* pp[2] = {dx0, dx1};
+  const float* dcat = nullptr;       // [C*Se,128]
+  TPC_TRY(enc_stack_backward(cx, L.enc.joint, a.joint, a.cat, C, Se, MaskRef{mha_mask, S, 0, N, r0}, d_enc, RowMap{Se, Se, 0},
+                             pp, s, &dcat));
+  float* other = dcat == dx0 ? dx1 : dx0;      // free ping-pong buffer
+  float* third = const_cast<float*>(d_enc);    // d_enc is consumed: reuse as a third buffer
+  float* bufs[2] = {other, third};
+  const float* dc = nullptr;
   // bins stack
-  {
-    const float* dc = dcat;
-    RowMap dm{N, Se, 0};
-    float* bufs[2] = {other, third};
-    int bi = 0;
-    for (int i = nl - 1; i >= 0; --i) {
-      const float* x = i == 0 ? a.emb_b : a.bins[i - 1].out2;
-      TPC_TRY(enc_layer_backward(cx, L.enc.bins[i], x, C, N, MaskRef{mha_mask, S, 0}, a.bins[i], dc, dm, bufs[bi], s));
-      dc = bufs[bi];
-      dm = RowMap{N, N, 0};
-      bi ^= 1;
-    }
-    const DenseP& eb = L.enc.emb1;
-    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, dc, eb.in, cx.G + eb.w, cx.G + eb.b, cx.st));
-  }
+  TPC_TRY(enc_stack_backward(cx, L.enc.bins, a.bins, a.emb_b, C, N, MaskRef{mha_mask, S, 0}, dcat, RowMap{N, Se, 0}, bufs, s, &dc));
+  const DenseP& eb = L.enc.emb1;
+  RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, dc, eb.in, cx.G + eb.w, cx.G + eb.b, cx.st));
   // resources stack
-  {
-    const float* dc = dcat;
-    RowMap dm{Re, Se, N};
-    float* bufs[2] = {other, third};
-    int bi = 0;
-    for (int i = nl - 1; i >= 0; --i) {
-      const float* x = i == 0 ? a.emb_r : a.res[i - 1].out2;
-      TPC_TRY(enc_layer_backward(cx, L.enc.res[i], x, C, Re, MaskRef{mha_mask, S, N + r0}, a.res[i], dc, dm, bufs[bi], s));
-      dc = bufs[bi];
-      dm = RowMap{Re, Re, 0};
-      bi ^= 1;
-    }
-    const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
-    RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, dc, er.in, cx.G + er.w, cx.G + er.b, cx.st));
-  }
+  TPC_TRY(enc_stack_backward(cx, L.enc.res, a.res, a.emb_r, C, Re, MaskRef{mha_mask, S, N + r0}, dcat, RowMap{Re, Se, N}, bufs, s,
+                             &dc));
+  const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
+  RUN(small_dense_bwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, dc, er.in, cx.G + er.w, cx.G + er.b, cx.st));
   return TPC_OK;
 }
 

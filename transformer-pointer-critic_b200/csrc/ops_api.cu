@@ -166,6 +166,21 @@ int tpc_gemm(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, f
   return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, N, K, e, k_splits, h->num_sms, (cudaStream_t)stream, Bt_corr);
 }
 
+int tpc_gemm_ln_bwd(tpc_handle* h, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int K,
+                    const float* aux, int ldaux, const float* y, const float* rstd, const float* gamma,
+                    const float* beta, float* dgamma, float* dbeta, void* stream) {
+  if (!h || !A || !Bt || !D || !y || !rstd || !gamma || !beta || !dgamma || !dbeta) return TPC_ERR_ARG;
+  GemmEpi e;
+  if (aux) { e.aux = aux; e.ldaux = ldaux; e.aux_mode = 1; }
+  e.gamma = gamma;
+  e.beta = beta;
+  e.lnb_y = y;
+  e.lnb_rstd = rstd;
+  e.lnb_dgamma = dgamma;
+  e.lnb_dbeta = dbeta;
+  return launch_gemm(h->tmaps, A, lda, Bt, ldb, D, ldd, M, 128, K, e, 1, h->num_sms, (cudaStream_t)stream, nullptr);
+}
+
 int tpc_gemm_split_image(tpc_handle* h, const float* Bt, int ldb, int N, int K, void* image, void* stream) {
   if (!h) return TPC_ERR_ARG;
   return build_split_image(Bt, ldb, N, K, image, (cudaStream_t)stream);
