@@ -200,6 +200,11 @@ typedef struct tpc_rollout_buffers {
 int tpc_rollout(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
                 const tpc_rollout_buffers* buf, int B, int num_bins, int num_resources, int greedy, uint64_t seed,
                 int64_t episode_id0, int64_t epoch, void* workspace, size_t workspace_bytes, void* stream);
+/* The loop over the T decoding steps (agents/trainer.py:49-100) is replayed as ONE CUDA graph from the second call with
+ * the same arguments on (every kernel argument of the loop is a function of the call's arguments; the Philox draw index
+ * epoch * T is read from device memory). Returns how many rollouts of this model ran as a graph replay.
+ * TPC_ROLLOUT_GRAPH=0 in the environment keeps plain stream launches. */
+unsigned long long tpc_rollout_graph_replays(const tpc_model* m);
 
 /* ------------------------------------------------------------------------------------------------------
  * CVRP (environment/custom/vrp/env.py; BASELINE config #5). State (B, Nn + V, 3) fp32: rows [0, Nn) nodes [x, y, demand]

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) decide_step_kernel(const DecideArgs a) {
   if (threadIdx.x == 0) {
     // the draw runs over the compact probabilities: the tokens left out have probability exactly 0, so the inverse-CDF
     // pick over the full row is the same token
-    const int pick = a.greedy ? best : a.win.full(sample_pick(sl, Sc, a.seed, a.id0 + c, a.draw));
+    const int pick = a.greedy ? best : a.win.full(sample_pick(sl, Sc, a.seed, a.id0 + c, a.draw + (a.draw0 ? *a.draw0 : 0)));
     a.actions[c] = pick;
     pick_s = pick;
   }

@@ -17,6 +17,7 @@ struct DecideArgs {
   int greedy;
   uint64_t seed;
   int64_t id0, draw;
+  const int64_t* draw0;    // optional device scalar added to `draw` (graph replay of the rollout: epoch * T lives here)
   int32_t* actions;        // (C) slot of this step
   // environment (live state, in place)
   tpc_env_config env;

@@ -271,6 +271,7 @@ int tpc_model_create(tpc_handle* h, const tpc_model_config* cfg, tpc_model** out
 
 int tpc_model_destroy(tpc_model* m) {
   if (!m) return TPC_OK;
+  if (m->rollout_graphs && m->rollout_graphs_free) m->rollout_graphs_free(m->rollout_graphs);
   cudaFree(m->d_actor_jobs);
   cudaFree(m->d_critic_jobs);
   for (int w = 0; w < 2; ++w) {

@@ -101,4 +101,7 @@ struct tpc_model {
   int n_chunks[2] = {0, 0};
   int n_tensors[2] = {0, 0};
   float* d_norms[2] = {nullptr, nullptr};
+  // cached CUDA graphs of the rollout's step loop (net.cu: RolloutGraphs), released through the function beside it
+  void* rollout_graphs = nullptr;
+  void (*rollout_graphs_free)(void*) = nullptr;
 };

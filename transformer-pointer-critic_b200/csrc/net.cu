@@ -8,6 +8,7 @@
 //   Decoder.call            actor/decoder.py:62-101        -> decoder_forward / decoder_backward
 //   CriticTransformer.call  critic/model.py:55-85          -> critic_forward / critic_backward
 //   trainer loop            agents/trainer.py:49-156       -> tpc_rollout / tpc_a2c_grads
+#include <cstring>
 #include <vector>
 
 #include "model.cuh"
@@ -588,6 +589,66 @@ int a2c_grads_impl(tpc_model* m, const float* actor_shadow, const float* actor_p
   return TPC_OK;
 }
 
+// ---- cached CUDA graphs of the rollout's step loop (see rollout_impl)
+struct RolloutKey {
+  tpc_env_config env;
+  const void* p[15];
+  size_t ws_bytes;
+  uint64_t seed;
+  int64_t id0;
+  int B, N, R, greedy, drop;
+};
+struct RolloutGraphs {
+  struct Slot { RolloutKey key; cudaGraphExec_t exec = nullptr; int seen = 0; unsigned long long stamp = 0, nodes = 0; };
+  std::vector<Slot> slots;
+  cudaStream_t cap_stream = nullptr;
+  int64_t* d_draw0 = nullptr;
+  unsigned long long clock = 0, replays = 0;
+  bool broken = false;   // a capture failed once: stream launches from then on
+  // the slot of this argument set (created, or recycled from the least recently used one, when it is new)
+  Slot* find(const RolloutKey& k) {
+    ++clock;
+    for (Slot& s : slots)
+      if (memcmp(&s.key, &k, sizeof(k)) == 0) { s.stamp = clock; return &s; }
+    if (slots.size() < 8) {
+      slots.emplace_back();
+    } else {
+      size_t lru = 0;
+      for (size_t i = 1; i < slots.size(); ++i) if (slots[i].stamp < slots[lru].stamp) lru = i;
+      if (slots[lru].exec) cudaGraphExecDestroy(slots[lru].exec);
+      std::swap(slots[lru], slots.back());
+      slots.back() = Slot();
+    }
+    Slot& s = slots.back();
+    s.key = k; s.stamp = clock;
+    return &s;
+  }
+};
+// TPC_ROLLOUT_GRAPH=0 keeps the stream launches (A / B runs, debugging)
+RolloutGraphs* rollout_graphs(tpc_model* m) {
+  const char* v = getenv("TPC_ROLLOUT_GRAPH");   // read per call: tests switch it inside one process
+  if (v && v[0] == '0') return nullptr;
+  if (!m->rollout_graphs) {
+    RolloutGraphs* rg = new RolloutGraphs();
+    if (cudaStreamCreateWithFlags(&rg->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&rg->d_draw0, sizeof(int64_t)) != cudaSuccess) {
+      cudaGetLastError();
+      if (rg->cap_stream) cudaStreamDestroy(rg->cap_stream);
+      delete rg;
+      return nullptr;
+    }
+    m->rollout_graphs = rg;
+    m->rollout_graphs_free = [](void* p) {
+      RolloutGraphs* g = static_cast<RolloutGraphs*>(p);
+      for (auto& s : g->slots) if (s.exec) cudaGraphExecDestroy(s.exec);
+      cudaStreamDestroy(g->cap_stream);
+      cudaFree(g->d_draw0);
+      delete g;
+    };
+  }
+  return static_cast<RolloutGraphs*>(m->rollout_graphs);
+}
+
 int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
                  const tpc_rollout_buffers* buf, int B, int N, int R, int greedy, uint64_t seed, int64_t id0,
                  int64_t epoch, Arena& ar, void* stream) {
@@ -627,33 +688,91 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
     TPC_CHECK_CUDA(cudaStreamSynchronize(st));
     drop = h_flag >= R;
   }
-  for (int t = 0; t < T; ++t) {
-    ar.off = mark;
-    Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, stream);
-    DecideArgs da{};
-    if (!ar.dry) {
-      da.greedy = greedy; da.seed = seed; da.id0 = id0; da.draw = epoch * T + t;
-      da.actions = buf->actions + (size_t)t * B;
-      da.env = *e;
-      da.batch = buf->batch; da.bin_mask = buf->bin_net_mask; da.mha_mask = buf->mha_mask; da.is_empty = buf->is_empty;
-      da.N = N; da.R = R; da.t = t; da.T = T; da.req = req_at(t); da.req_next = req_at(t + 1 < T ? t + 1 : t);
-      da.rewards = buf->rewards;
-      if (t + 1 < T) {
-        da.dec_next = dec_at(t + 1);
-        da.pmask_next = pmask_at(t + 1);
-        da.states_next = buf->states ? buf->states + (size_t)(t + 1) * B * S * F : nullptr;
-        da.mha_next = buf->mha_masks ? buf->mha_masks + (size_t)(t + 1) * B * S : nullptr;
-        da.is_empties_next = (buf->is_empties && buf->is_empty) ? buf->is_empties + (size_t)(t + 1) * B * S : nullptr;
+  // The T decoding steps. draw0 == nullptr: the Philox draw index epoch * T + t is a kernel argument; otherwise the
+  // kernels read epoch * T from *draw0 (graph replay: everything else about a step is the same from call to call).
+  auto run_steps = [&](cudaStream_t rs, const int64_t* draw0) -> int {
+    for (int t = 0; t < T; ++t) {
+      ar.off = mark;
+      Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, rs);
+      DecideArgs da{};
+      if (!ar.dry) {
+        da.greedy = greedy; da.seed = seed; da.id0 = id0;
+        da.draw = draw0 ? t : epoch * T + t;
+        da.draw0 = draw0;
+        da.actions = buf->actions + (size_t)t * B;
+        da.env = *e;
+        da.batch = buf->batch; da.bin_mask = buf->bin_net_mask; da.mha_mask = buf->mha_mask; da.is_empty = buf->is_empty;
+        da.N = N; da.R = R; da.t = t; da.T = T; da.req = req_at(t); da.req_next = req_at(t + 1 < T ? t + 1 : t);
+        da.rewards = buf->rewards;
+        if (t + 1 < T) {
+          da.dec_next = dec_at(t + 1);
+          da.pmask_next = pmask_at(t + 1);
+          da.states_next = buf->states ? buf->states + (size_t)(t + 1) * B * S * F : nullptr;
+          da.mha_next = buf->mha_masks ? buf->mha_masks + (size_t)(t + 1) * B * S : nullptr;
+          da.is_empties_next = (buf->is_empties && buf->is_empty) ? buf->is_empties + (size_t)(t + 1) * B * S : nullptr;
+        }
       }
+      ActorActs a;
+      StateRef sr{buf->batch, F, buf->is_empty};
+      TPC_TRY(actor_forward(cx, sr, ar.dry ? nullptr : dec_at(t), ar.dry ? nullptr : pmask_at(t), buf->mha_mask, B, N, R, a,
+                            buf->logits ? buf->logits + (size_t)t * B * S : nullptr, nullptr, nullptr, &da, drop ? t : 0));
+      if (!ar.fits()) return TPC_ERR_WORKSPACE;
+      if (ar.dry) break;
     }
-    ActorActs a;
-    StateRef sr{buf->batch, F, buf->is_empty};
-    TPC_TRY(actor_forward(cx, sr, ar.dry ? nullptr : dec_at(t), ar.dry ? nullptr : pmask_at(t), buf->mha_mask, B, N, R, a,
-                          buf->logits ? buf->logits + (size_t)t * B * S : nullptr, nullptr, nullptr, &da, drop ? t : 0));
-    if (!ar.fits()) return TPC_ERR_WORKSPACE;
-    if (ar.dry) break;
+    return TPC_OK;
+  };
+  if (ar.dry) return run_steps(st, nullptr);
+
+  // ---- CUDA-graph replay of the step loop (T x ~22 launches; launch-bound for small batches). Every kernel argument
+  // of the loop is a function of the call's arguments alone (workspace offsets, trajectory slots, tensor maps), except
+  // the Philox draw index, which the graph reads from device memory. A call whose arguments match a cached graph
+  // replays it; a graph is built the second time an argument set is seen (one-off callers never pay for a capture).
+  RolloutGraphs* rg = rollout_graphs(m);
+  if (!rg) return run_steps(st, nullptr);
+  RolloutKey key;
+  memset(&key, 0, sizeof(key));   // padding bytes take part in the comparison
+  key.env = *e;
+  key.p[0] = actor_shadow; key.p[1] = actor_params; key.p[2] = ar.base; key.p[3] = buf->batch; key.p[4] = buf->bin_net_mask;
+  key.p[5] = buf->mha_mask; key.p[6] = buf->is_empty; key.p[7] = buf->states; key.p[8] = buf->dec_inputs;
+  key.p[9] = buf->ptr_masks; key.p[10] = buf->mha_masks; key.p[11] = buf->is_empties; key.p[12] = buf->actions;
+  key.p[13] = buf->rewards; key.p[14] = buf->logits;
+  key.ws_bytes = ar.size; key.seed = seed; key.id0 = id0;
+  key.B = B; key.N = N; key.R = R; key.greedy = greedy; key.drop = drop ? 1 : 0;
+  RolloutGraphs::Slot* slot = rg->find(key);
+  if (slot && !slot->exec && slot->seen >= 1 && !rg->broken) {
+    // capture on the cache's own non-blocking stream (the caller's may be the legacy default stream, which cannot be
+    // captured); nothing executes during capture, so no ordering with `st` is needed until the launch below
+    TPC_TRY(gemm_tc_init());
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(rg->cap_stream, cudaStreamCaptureModeThreadLocal);
+    int rc = TPC_OK;
+    if (ce == cudaSuccess) {
+      const unsigned long long l0 = g_tpc_launches;
+      rc = run_steps(rg->cap_stream, rg->d_draw0);
+      slot->nodes = g_tpc_launches - l0;   // recorded, not launched: counted per replay below (tpc_launch_count)
+      g_tpc_launches = l0;
+      ce = cudaStreamEndCapture(rg->cap_stream, &graph);
+    }
+    if (ce == cudaSuccess && rc == TPC_OK && graph) ce = cudaGraphInstantiate(&slot->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != TPC_OK || !slot->exec) {
+      fprintf(stderr, "[tpc] rollout graph capture failed (%s, rc %d): falling back to stream launches\n",
+              cudaGetErrorString(ce), rc);
+      cudaGetLastError();
+      slot->exec = nullptr;
+      rg->broken = true;
+    }
   }
-  return TPC_OK;
+  if (slot && slot->exec) {
+    const int64_t draw_base = epoch * T;
+    TPC_CHECK_CUDA(cudaMemcpyAsync(rg->d_draw0, &draw_base, sizeof(draw_base), cudaMemcpyHostToDevice, st));
+    TPC_CHECK_CUDA(cudaGraphLaunch(slot->exec, st));
+    g_tpc_launches += slot->nodes;
+    ++rg->replays;
+    return TPC_OK;
+  }
+  if (slot) ++slot->seen;
+  return run_steps(st, nullptr);
 }
 
 }  // namespace
@@ -742,6 +861,10 @@ int tpc_rollout(tpc_model* m, const tpc_env_config* e, const float* actor_shadow
   ar.base = (char*)workspace; ar.size = workspace_bytes;
   return rollout_impl(m, e, actor_shadow, actor_params, buf, B, num_bins, num_resources, greedy, seed, episode_id0,
                       epoch, ar, stream);
+}
+
+unsigned long long tpc_rollout_graph_replays(const tpc_model* m) {
+  return (m && m->rollout_graphs) ? static_cast<const RolloutGraphs*>(m->rollout_graphs)->replays : 0;
 }
 
 int tpc_a2c_grads(tpc_model* m, const float* actor_shadow, const float* actor_params, const float* critic_shadow,

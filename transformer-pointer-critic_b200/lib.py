@@ -51,6 +51,7 @@ SIGNATURES = {
     "tpc_destroy": (c_int, [c_void_p]),
     "tpc_num_sms": (c_int, [c_void_p]),
     "tpc_launch_count": (C.c_ulonglong, []),
+    "tpc_rollout_graph_replays": (C.c_ulonglong, [C.c_void_p]),
     "tpc_model_create": (c_int, [c_void_p, C.POINTER(ModelConfig), C.POINTER(c_void_p)]),
     "tpc_model_destroy": (c_int, [c_void_p]),
     "tpc_param_count": (c_size_t, [c_void_p, c_int]),
