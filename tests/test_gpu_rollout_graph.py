@@ -9,12 +9,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _rollouts(graph: bool, n_calls: int, batch: int, nodes: int, rules: int, greedy: bool):
+def _rollouts(graph: bool, n_calls: int, batch: int, nodes: int, rules: int, greedy: bool, fork: int = 1):
     import torch
     from tpc_b200.agent import Agent
     from tpc_b200.configs import get_configs
     from tpc_b200.env import ResourceEnvironmentV3
     os.environ["TPC_ROLLOUT_GRAPH"] = "1" if graph else "0"
+    os.environ["TPC_ROLLOUT_FORK"] = str(fork)
     try:
         agent_cfg, _, env_cfg, _, _, _ = get_configs("ResourceV3", "tpc")
         env_cfg = json.loads(json.dumps(env_cfg))
@@ -35,14 +36,15 @@ def _rollouts(graph: bool, n_calls: int, batch: int, nodes: int, rules: int, gre
         return out, replays
     finally:
         os.environ.pop("TPC_ROLLOUT_GRAPH", None)
+        os.environ.pop("TPC_ROLLOUT_FORK", None)
 
 
 @pytest.mark.parametrize("batch,nodes,rules,greedy", [(16, 5, 9, False), (128, 10, 20, False), (64, 50, 100, True)])
 def test_graph_replay_equals_stream_launches_bit_for_bit(batch, nodes, rules, greedy):
     import torch
     n_calls = 4
-    ref, r0 = _rollouts(False, n_calls, batch, nodes, rules, greedy)
-    got, r1 = _rollouts(True, n_calls, batch, nodes, rules, greedy)
+    ref, r0 = _rollouts(False, n_calls, batch, nodes, rules, greedy, fork=0)   # one stream, plain launches
+    got, r1 = _rollouts(True, n_calls, batch, nodes, rules, greedy, fork=2)    # graph replay with the two-stream fork
     assert r0 == 0
     assert r1 == n_calls - 1, r1          # call 1 runs on the stream, call 2 captures and replays, 3.. replay
     for i, (a, b) in enumerate(zip(ref, got)):
@@ -50,3 +52,13 @@ def test_graph_replay_equals_stream_launches_bit_for_bit(batch, nodes, rules, gr
             assert torch.equal(a[k], b[k]), (i, k)
     if not greedy:   # sampled rollouts of different epochs must differ (the draw index really advances under replay)
         assert not torch.equal(got[1]["actions"], got[2]["actions"]) or not torch.equal(got[1]["batch"], got[2]["batch"])
+
+
+def test_two_stream_encoder_fork_equals_one_stream_bit_for_bit():
+    """encoder_forward's fork / join (rules stack on a second stream beside the nodes stack) without a graph."""
+    import torch
+    ref, _ = _rollouts(False, 2, 32, 10, 20, False, fork=0)
+    got, _ = _rollouts(False, 2, 32, 10, 20, False, fork=2)
+    for a, b in zip(ref, got):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k

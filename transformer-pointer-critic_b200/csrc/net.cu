@@ -42,9 +42,31 @@ struct Ctx {
   float* G;         // canonical gradient accumulator (nullptr in forward-only calls)
   Arena* ar;
   cudaStream_t st;
+  const struct SideStream* side = nullptr;   // rollout only: second stream for the two independent encoder stacks
   bool dry() const { return ar->dry; }
   TmapCache* tc() const { return m->h->tmaps; }
   int sms() const { return m->h->num_sms; }
+};
+
+inline int rollout_fork_mode() {   // read per call: tests switch it inside one process
+  const char* v = getenv("TPC_ROLLOUT_FORK");
+  return v ? atoi(v) : 1;
+}
+// fork / join helper: work issued on `stream` between fork() and join() runs beside the caller's stream (also while
+// that stream is being captured into a graph: the event pair becomes two graph edges)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int fork(cudaStream_t main) const {
+    TPC_CHECK_CUDA(cudaEventRecord(ev_fork, main));
+    TPC_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_fork, 0));
+    return TPC_OK;
+  }
+  int join(cudaStream_t main) const {
+    TPC_CHECK_CUDA(cudaEventRecord(ev_join, stream));
+    TPC_CHECK_CUDA(cudaStreamWaitEvent(main, ev_join, 0));
+    return TPC_OK;
+  }
 };
 
 struct MaskRef { const float* mask; int mS; int m0; int split = 1 << 30; int gap = 0; };  // mask[c * mS + m0 + (j < split ? j : j + gap)]
@@ -237,22 +259,33 @@ int encoder_forward(Ctx& cx, StateRef sr, const float* mha_mask, int C, int N, i
   a.emb_r = ar.f((size_t)C * Re * 128);
   const DenseP& eb = L.enc.emb1;
   const DenseP& er = L.enc.common ? L.enc.emb1 : L.enc.emb2;
-  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, cx.P + eb.w, cx.P + eb.b, eb.in, a.emb_b, cx.st));
-  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, cx.P + er.w, cx.P + er.b, er.in, a.emb_r, cx.st));
+  // The nodes stack and the rules stack are independent until the concatenation: the rollout runs the rules stack on a
+  // second stream beside the nodes stack (TPC_ROLLOUT_FORK=0: one stream). Small batches leave most SMs idle in every
+  // kernel of a stack (config #1: 11.98 -> 11.38 ms per iteration); at batch 1024 the two stacks fill each other's tails
+  // (greedy decode of the tester cell 79.3 -> 77.4 ms).
+  const bool fork = cx.side && !cx.dry() && rollout_fork_mode() != 0;
+  Ctx cr = cx;                       // context of the rules stack
+  if (fork) {
+    cr.st = cx.side->stream;
+    TPC_TRY(cx.side->fork(cx.st));
+  }
   a.bins.resize(nl); a.res.resize(nl); a.joint.resize(nl);
+  a.cat = ar.f((size_t)C * Se * 128);
+  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * N, RowMap{N, S, 0}, cx.P + eb.w, cx.P + eb.b, eb.in, a.emb_b, cx.st));
   const float* xb = a.emb_b;
   for (int i = 0; i < nl; ++i) {
     TPC_TRY(enc_layer_forward(cx, L.enc.bins[i], xb, C, N, MaskRef{mha_mask, S, 0}, a.bins[i]));
     xb = a.bins[i].out2;
   }
+  RUN(scatter_rows(xb, C * N, RowMap{N, Se, 0}, a.cat, cx.st));
+  RUN(small_dense_fwd(sr.state, sr.ld, sr.extra, C * Re, RowMap{Re, S, N + r0}, cx.P + er.w, cx.P + er.b, er.in, a.emb_r, cr.st));
   const float* xr = a.emb_r;
   for (int i = 0; i < nl; ++i) {
-    TPC_TRY(enc_layer_forward(cx, L.enc.res[i], xr, C, Re, MaskRef{mha_mask, S, N + r0}, a.res[i]));
+    TPC_TRY(enc_layer_forward(cr, L.enc.res[i], xr, C, Re, MaskRef{mha_mask, S, N + r0}, a.res[i]));
     xr = a.res[i].out2;
   }
-  a.cat = ar.f((size_t)C * Se * 128);
-  RUN(scatter_rows(xb, C * N, RowMap{N, Se, 0}, a.cat, cx.st));
-  RUN(scatter_rows(xr, C * Re, RowMap{Re, Se, N}, a.cat, cx.st));
+  RUN(scatter_rows(xr, C * Re, RowMap{Re, Se, N}, a.cat, cr.st));
+  if (fork) TPC_TRY(cx.side->join(cx.st));
   const float* xj = a.cat;
   for (int i = 0; i < nl; ++i) {
     TPC_TRY(enc_layer_forward(cx, L.enc.joint[i], xj, C, Se, MaskRef{mha_mask, S, 0, N, r0}, a.joint[i]));
@@ -596,7 +629,7 @@ struct RolloutKey {
   size_t ws_bytes;
   uint64_t seed;
   int64_t id0;
-  int B, N, R, greedy, drop;
+  int B, N, R, greedy, drop, fork_mode;
 };
 struct RolloutGraphs {
   struct Slot { RolloutKey key; cudaGraphExec_t exec = nullptr; int seen = 0; unsigned long long stamp = 0, nodes = 0; };
@@ -605,6 +638,8 @@ struct RolloutGraphs {
   int64_t* d_draw0 = nullptr;
   unsigned long long clock = 0, replays = 0;
   bool broken = false;   // a capture failed once: stream launches from then on
+  bool unusable = false; // streams / events could not be created
+  SideStream side_cap, side_run;   // second stream of the encoder fork / join: under capture, on the caller's stream
   // the slot of this argument set (created, or recycled from the least recently used one, when it is new)
   Slot* find(const RolloutKey& k) {
     ++clock;
@@ -624,29 +659,41 @@ struct RolloutGraphs {
     return &s;
   }
 };
-// TPC_ROLLOUT_GRAPH=0 keeps the stream launches (A / B runs, debugging)
+// per-model rollout state: graph cache, capture stream, the side streams of encoder_forward's fork / join
 RolloutGraphs* rollout_graphs(tpc_model* m) {
-  const char* v = getenv("TPC_ROLLOUT_GRAPH");   // read per call: tests switch it inside one process
-  if (v && v[0] == '0') return nullptr;
   if (!m->rollout_graphs) {
     RolloutGraphs* rg = new RolloutGraphs();
-    if (cudaStreamCreateWithFlags(&rg->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&rg->d_draw0, sizeof(int64_t)) != cudaSuccess) {
-      cudaGetLastError();
-      if (rg->cap_stream) cudaStreamDestroy(rg->cap_stream);
-      delete rg;
-      return nullptr;
-    }
+    bool ok = cudaStreamCreateWithFlags(&rg->cap_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&rg->d_draw0, sizeof(int64_t)) == cudaSuccess;
+    for (SideStream* sd : {&rg->side_cap, &rg->side_run})
+      ok = ok && cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&sd->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&sd->ev_join, cudaEventDisableTiming) == cudaSuccess;
     m->rollout_graphs = rg;
     m->rollout_graphs_free = [](void* p) {
       RolloutGraphs* g = static_cast<RolloutGraphs*>(p);
       for (auto& s : g->slots) if (s.exec) cudaGraphExecDestroy(s.exec);
-      cudaStreamDestroy(g->cap_stream);
+      for (SideStream* sd : {&g->side_cap, &g->side_run}) {
+        if (sd->ev_fork) cudaEventDestroy(sd->ev_fork);
+        if (sd->ev_join) cudaEventDestroy(sd->ev_join);
+        if (sd->stream) cudaStreamDestroy(sd->stream);
+      }
+      if (g->cap_stream) cudaStreamDestroy(g->cap_stream);
       cudaFree(g->d_draw0);
       delete g;
     };
+    if (!ok) {
+      cudaGetLastError();
+      rg->unusable = true;
+    }
   }
-  return static_cast<RolloutGraphs*>(m->rollout_graphs);
+  RolloutGraphs* rg = static_cast<RolloutGraphs*>(m->rollout_graphs);
+  return rg->unusable ? nullptr : rg;
+}
+// TPC_ROLLOUT_GRAPH=0 keeps the stream launches (A / B runs, debugging); read per call: tests switch it inside one process
+bool rollout_graph_wanted() {
+  const char* v = getenv("TPC_ROLLOUT_GRAPH");
+  return !(v && v[0] == '0');
 }
 
 int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
@@ -690,10 +737,12 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
   }
   // The T decoding steps. draw0 == nullptr: the Philox draw index epoch * T + t is a kernel argument; otherwise the
   // kernels read epoch * T from *draw0 (graph replay: everything else about a step is the same from call to call).
+  RolloutGraphs* rg = ar.dry ? nullptr : rollout_graphs(m);
   auto run_steps = [&](cudaStream_t rs, const int64_t* draw0) -> int {
     for (int t = 0; t < T; ++t) {
       ar.off = mark;
       Ctx cx = make_ctx(m, 0, actor_params, actor_shadow, nullptr, &ar, rs);
+      if (rg) cx.side = draw0 ? &rg->side_cap : &rg->side_run;
       DecideArgs da{};
       if (!ar.dry) {
         da.greedy = greedy; da.seed = seed; da.id0 = id0;
@@ -727,8 +776,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
   // of the loop is a function of the call's arguments alone (workspace offsets, trajectory slots, tensor maps), except
   // the Philox draw index, which the graph reads from device memory. A call whose arguments match a cached graph
   // replays it; a graph is built the second time an argument set is seen (one-off callers never pay for a capture).
-  RolloutGraphs* rg = rollout_graphs(m);
-  if (!rg) return run_steps(st, nullptr);
+  if (!rg || !rollout_graph_wanted()) return run_steps(st, nullptr);
   RolloutKey key;
   memset(&key, 0, sizeof(key));   // padding bytes take part in the comparison
   key.env = *e;
@@ -737,7 +785,7 @@ int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shado
   key.p[9] = buf->ptr_masks; key.p[10] = buf->mha_masks; key.p[11] = buf->is_empties; key.p[12] = buf->actions;
   key.p[13] = buf->rewards; key.p[14] = buf->logits;
   key.ws_bytes = ar.size; key.seed = seed; key.id0 = id0;
-  key.B = B; key.N = N; key.R = R; key.greedy = greedy; key.drop = drop ? 1 : 0;
+  key.B = B; key.N = N; key.R = R; key.greedy = greedy; key.drop = drop ? 1 : 0; key.fork_mode = rollout_fork_mode();
   RolloutGraphs::Slot* slot = rg->find(key);
   if (slot && !slot->exec && slot->seen >= 1 && !rg->broken) {
     // capture on the cache's own non-blocking stream (the caller's may be the legacy default stream, which cannot be
