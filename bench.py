@@ -78,6 +78,9 @@ def dataflow_bytes_per_state(N, R, B=1024, chunk=10240, actor=(1, 128), critic=(
       forward  : QKV 1+3, attention 3+1, O-proj + LN 1+1+1, FFN1 1+m, FFN2 + LN m+1+1             = 14 + 2m
       backward : 2 x LN 3, dW2 m+1, dH 1+m, dW1 1+m, d(out1) m+1+1, dWo 2, d(att) 2, attention 3+1+1+3, dWqkv 1+3,
                  dx 3+1+1                                                                          = 32 + 4m
+                 LayerNorm 1 backward rides in the epilogue of the d(out1) GEMM (-3 for ln_bwd, +1 for the saved
+                 LayerNorm output the epilogue reads) and LayerNorm 2 backward in the dx GEMM of the layer above it,
+                 for every layer but the top one of a stack                              = 30 + 4m - 2 (layers - 1) / layers
     times the tokens of the three stacks (bins N, rules R, joint N + R) x layers. The critic keeps every token; the
     actor leaves out the rule tokens placed before the first step of its chunk (token windows): chunk k of `chunk`
     states drops floor(k * chunk / B) rules, the rollout step t drops t. The actor's decoder adds the K2|V2|W2e
@@ -91,7 +94,7 @@ def dataflow_bytes_per_state(N, R, B=1024, chunk=10240, actor=(1, 128), critic=(
     def encoder(layers, dff, rules):
         m = dff // d
         tokens = N + rules + (N + rules)                      # bins stack + rules stack + joint stack
-        return tokens * layers, (14 + 2 * m), (32 + 4 * m)
+        return tokens * layers, (14 + 2 * m), (30 + 4 * m - 2 * (layers - 1) / layers)
     tl, f, b = encoder(*critic, R)
     total = tl * (f + b) * u
     tl, f, b = encoder(*actor, kept_update)
