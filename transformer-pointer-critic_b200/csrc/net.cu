@@ -691,9 +691,14 @@ RolloutGraphs* rollout_graphs(tpc_model* m) {
   return rg->unusable ? nullptr : rg;
 }
 // TPC_ROLLOUT_GRAPH=0 keeps the stream launches (A / B runs, debugging); read per call: tests switch it inside one process
+// Under a CUDA injection tool (Nsight Compute, compute-sanitizer: CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_* in the
+// environment) the loop stays on the stream as well: ncu cannot profile launches that are being captured and shuts the
+// process down (seen with `ncu --metrics gpu__time_duration.sum python bench.py`), and a profile should list the kernels.
 bool rollout_graph_wanted() {
   const char* v = getenv("TPC_ROLLOUT_GRAPH");
-  return !(v && v[0] == '0');
+  if (v && v[0] == '0') return false;
+  if (v && v[0] == '2') return true;   // forced (debugging the capture path under a tool)
+  return !getenv("CUDA_INJECTION64_PATH") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
 }
 
 int rollout_impl(tpc_model* m, const tpc_env_config* e, const float* actor_shadow, const float* actor_params,
