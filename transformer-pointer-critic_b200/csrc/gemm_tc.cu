@@ -123,6 +123,7 @@ struct GemmArgs {
   float* atomic_out;
   int ld_out;
   int aux_mode, relu, ln, round_out, atomic;
+  int aux_pf;  // LayerNorm epilogues: L2 prefetch of the next tile's residual boxes one tile ahead (TPC_AUX_PREFETCH=0: off)
   int split;   // fp32-accurate FP16 split product (see the file header): activation halves built on chip, weight halves from the image
   float ln_eps;
   uint32_t* mask_out;         // ReLU bit image (weight-resident kernel, MASK template variants)
@@ -429,6 +430,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_t * BM + et;
+      // The staging tile serves as residual input AND as output, so the residual of the next tile can only be requested
+      // once this tile's store has read it out: that load's latency is exposed (and binds the K = 128 launches, whose
+      // main loop is shorter than the epilogue). An L2 prefetch one tile ahead takes the HBM part out of it.
+      if (g.aux_mode && g.aux_pf && leader && item + step < g.num_items) {
+        const int nn = (item + step) % g.n_tiles, nm = ((item + step) / g.n_tiles) / g.k_splits;
+        for (int j = 0; j < 4; ++j) tma_prefetch_2d(&tmAux, nn * BN + j * BK, nm * BM);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (g.aux_mode) {
@@ -535,6 +543,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < 16; ++i) {
         const int r = m_t * BM + ew * 16 + i;
         yv[i] = r < g.M ? __ldg(reinterpret_cast<const float4*>(g.lnb_y + (size_t)r * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (g.aux_mode && g.aux_pf && leader && item + step < g.num_items) {   // see the LayerNorm forward epilogue
+        const int nm = (item + step) / g.n_tiles;
+        for (int j = 0; j < 4; ++j) tma_prefetch_2d(&tmAux, j * BK, nm * BM);
       }
       const int rl = m_t * BM + ew * 16 + (lane & 15);          // lane i (and i + 16) keeps 1/sigma of row i
       const float rs_lane = rl < g.M ? __ldg(g.lnb_rstd + rl) : 0.f;
@@ -1519,6 +1531,8 @@ int launch_gemm(TmapCache* tc, const float* A, int lda, const float* Bt, int ldb
   g.ln_eps = epi.ln_eps;
   g.lnb_y = epi.lnb_y; g.lnb_rstd = epi.lnb_rstd; g.lnb_dgamma = epi.lnb_dgamma; g.lnb_dbeta = epi.lnb_dbeta;
   g.split = Bt_corr ? 1 : 0;
+  static const int aux_pf = [] { const char* v = getenv("TPC_AUX_PREFETCH"); return (v && v[0] == '0') ? 0 : 1; }();
+  g.aux_pf = aux_pf;
   CUtensorMap tA, tB, tBlo, tAux, tD;
   TPC_TRY(get_tmap(tc, A, M, K, lda, BM, 0, &tA));
   TPC_TRY(get_tmap(tc, Bt, N, K, ldb, BN, 0, &tB));
