@@ -94,7 +94,7 @@ def dataflow_bytes_per_state(N, R, B=1024, chunk=10240, actor=(1, 128), critic=(
     def encoder(layers, dff, rules):
         m = dff // d
         tokens = N + rules + (N + rules)                      # bins stack + rules stack + joint stack
-        return tokens * layers, (14 + 2 * m), (30 + 4 * m - 2 * (layers - 1) / layers)
+        return tokens * layers, (14 + 2 * m), (30 + 4 * m - 2 * (layers - 1) / max(layers, 1))
     tl, f, b = encoder(*critic, R)
     total = tl * (f + b) * u
     tl, f, b = encoder(*actor, kept_update)
