@@ -46,7 +46,10 @@ def test_graph_replay_equals_stream_launches_bit_for_bit(batch, nodes, rules, gr
     ref, r0 = _rollouts(False, n_calls, batch, nodes, rules, greedy, fork=0)   # one stream, plain launches
     got, r1 = _rollouts(True, n_calls, batch, nodes, rules, greedy, fork=2)    # graph replay with the two-stream fork
     assert r0 == 0
-    assert r1 == n_calls - 1, r1          # call 1 runs on the stream, call 2 captures and replays, 3.. replay
+    # call 1 runs on the stream, call 2 captures and replays, 3.. replay -- unless a CUDA injection tool (profiler,
+    # tracer, sanitizer) is attached: the library then keeps stream launches (net.cu rollout_graph_wanted)
+    traced = any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
+    assert r1 == (0 if traced else n_calls - 1), r1
     for i, (a, b) in enumerate(zip(ref, got)):
         for k in a:
             assert torch.equal(a[k], b[k]), (i, k)
