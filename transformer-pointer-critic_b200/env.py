@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import lib as L
+from . import vrp_instances
 from .engine import REWARD_TYPES, RolloutTensors, env_config_struct
 
 
@@ -295,9 +296,13 @@ class CVRP:
     fused rollout uses (`device_buffers` / `reset_into` / `Agent.rollout`): step t serves node t + 1 (then the depot once
     per vehicle) and the pointer chooses the vehicle; every adapter step is one reference `step(vehicle, node)`.
 
-    The reference samples its batch from one Augerat instance file (`dir_path` / `problem_name`, :27-45); instance files
-    are out of scope here, so `reset` draws synthetic instances of the same form (integer coordinates 0..99, demands
-    1..`max_demand`, `vehicle_capacity`), and `load_batch` installs a given batch (e.g. one parsed elsewhere)."""
+    The reference samples its batch from one Augerat instance file (`dir_path` / `problem_name`, :27-45). When
+    `dir_path` holds that instance (`<name>.vrp.json` as the reference keeps it, or the bare `<name>.vrp`; the files are
+    not part of this repository) `reset` does the same: the depot, `node_sample_size - 1` distinct customers of the
+    instance and `vehicle_sample_size` vehicles of the instance's capacity per episode (`vrp_instances.py`; host NumPy,
+    seeded by (seed_value, first episode id, reset count)), and `optimum_value` is the file's optimum. Otherwise `reset`
+    draws synthetic instances of the same form on the device (integer coordinates 0..99, demands 1..`max_demand`,
+    `vehicle_capacity`). `load_batch` installs a given batch."""
     KIND = 2
 
     def __init__(self, name: str, opts: dict, device="cuda:0"):
@@ -319,7 +324,22 @@ class CVRP:
         cfg = L.EnvConfig()
         cfg.kind, cfg.num_features = self.KIND, 3
         self._cfg = cfg
+        # instance file (vrp/env.py:27-45) when it can be found, else synthetic instances
+        self.instance_name, self.optimum_value, self._tables = None, None, None
+        found = vrp_instances.load_problem(opts.get("dir_path"), opts.get("problem_name")) if opts.get("problem_name") else None
+        if found is not None:
+            problem, solution = found
+            self.instance_name, self.optimum_value = problem["name"], solution.get("cost")
+            self.vehicle_capacity = int(problem["capacity"])
+            self.total_demand = int(problem["total_demand"])
+            self._tables = vrp_instances.instance_tables(problem, 3)
         self.reset()
+
+    def _sample_instance_batch(self, batch_size=None) -> np.ndarray:
+        rng = np.random.default_rng([self.seed_value, self.episode_id0, self.epoch])
+        self.epoch += 1
+        return vrp_instances.sample_batch(self._tables, batch_size or self.batch_size, self.node_sample_size,
+                                          self.vehicle_sample_size, rng)
 
     # the names Agent.rollout / trainer-side code use for the two token segments
     @property
@@ -348,6 +368,8 @@ class CVRP:
 
     def reset(self):
         """:50-65."""
+        if self._tables is not None:
+            return self.load_batch(self._sample_instance_batch())
         self.visited_nodes = 0
         self._alloc()
         L.check(self.lib.tpc_cvrp_reset(self.h, self.seed_value, self.episode_id0, self.epoch, self.batch_size,
@@ -431,6 +453,12 @@ class CVRP:
                               store=store, keep_logits=keep_logits, T=self.steps)
 
     def reset_into(self, bufs: RolloutTensors) -> None:
+        if self._tables is not None:     # instance file: the batch comes from the host, the masks as cvrp_reset_kernel sets them
+            bufs.batch.copy_(torch.as_tensor(self._sample_instance_batch(bufs.B)))
+            bufs.bin_net_mask.zero_()
+            bufs.bin_net_mask[:, : bufs.N] = 1
+            bufs.mha_mask.zero_()
+            return
         L.check(self.lib.tpc_cvrp_reset(self.h, self.seed_value, self.episode_id0, self.epoch, bufs.B, bufs.N, bufs.R,
                                         self.max_demand, self.vehicle_capacity, L.ptr(bufs.batch),
                                         L.ptr(bufs.bin_net_mask), None, L.ptr(bufs.mha_mask), self.stream),
